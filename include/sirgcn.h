@@ -1,0 +1,175 @@
+/* sirgcn.h — C-ABI of the B200-native SIR-GCN convolution library (libsirgcn.so).
+ *
+ * The reference (briangodwinlim/SIR-GCN) has no FFI layer of its own: its hot path is
+ * models/conv.py executed by DGL + PyTorch.  Each entry point below names the reference
+ * call site (file:line under /root/reference) whose library behaviour it replaces.
+ *
+ * Conventions
+ *  - every pointer is a raw DEVICE pointer owned by the caller (PyTorch caching
+ *    allocator); the library never allocates or frees tensor memory and never
+ *    synchronises the device (exception: none — counts needed on the host are written
+ *    to device memory and the caller decides when to read them);
+ *  - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*);
+ *  - return value 0 = success, otherwise a negative SIRGCN_E* code or a positive
+ *    cudaError_t; sirgcn_last_error() returns a thread-local message;
+ *  - feature tables are row-major, `ld*` = row stride in ELEMENTS; every row start
+ *    must be 16-byte aligned (base pointer 16-B aligned, ld*sizeof(elem) % 16 == 0);
+ *    columns d..ld-1 of Q/K/E tables must hold zeros (they are read as padding);
+ *  - indices are int32; E < 2^31.
+ */
+#ifndef SIRGCN_H_
+#define SIRGCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIRGCN_ABI_VERSION 1
+
+/* element types of feature tables (accumulation is always fp32) */
+enum { SIRGCN_F32 = 0, SIRGCN_BF16 = 1, SIRGCN_F16 = 2 };
+/* activations σ applied in registers (conv.py:34 `activation`) */
+enum { SIRGCN_ACT_IDENTITY = 0, SIRGCN_ACT_RELU = 1, SIRGCN_ACT_LEAKY_RELU = 2, SIRGCN_ACT_GELU = 3 };
+/* error codes */
+enum {
+    SIRGCN_OK = 0,
+    SIRGCN_EINVAL = -1,   /* bad argument (shape, alignment, enum)          */
+    SIRGCN_ENOSPC = -2,   /* workspace too small                            */
+    SIRGCN_EUNSUP = -3    /* unsupported configuration (e.g. row too wide)  */
+};
+
+const char *sirgcn_last_error(void);
+int sirgcn_abi_version(void);
+/* number of kernels this library has launched in this process (bench `gpu_launches`) */
+uint64_t sirgcn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Graph index construction.  Replaces DGL's COO->CSR/CSC conversion and degree queries
+ * triggered by graph.in_degrees()/out_degrees() (conv.py:51-52) and update_all (conv.py:63).
+ *
+ * From COO (src[e] -> dst[e], e = edge id) build, by STABLE sort (ties keep edge-id order):
+ *   in-CSR  (destination-major): indptr_in[N+1], col_src[E], eid_in[E]
+ *   out-CSC (source-major)     : indptr_out[N+1], row_dst[E], eid_out[E]
+ * eid_in / eid_out may be NULL (then no edge-id permutation is produced).
+ * Per-node coefficients (any may be NULL):
+ *   in_norm[v]  = clamp(in_deg,1)^-1/2,  out_norm[v] = clamp(out_deg,1)^-1/2  (conv.py:54-57, 'sym')
+ *   inv_in_deg[v] = 1/clamp(in_deg,1)                                         (fn.mean, conv.py:41)
+ * Long-row schedule (rows with degree > long_threshold are split into chunks of
+ * long_threshold edges so that hubs are spread over many warps):
+ *   sched_*_long_rows[cap_long], sched_*_long_first[cap_long + 1 ... see below],
+ *   sched_*_chunk_lrow[cap_chunks], sched_*_chunk_beg[cap_chunks], counts[4] =
+ *   {n_long_in, n_chunks_in, n_long_out, n_chunks_out} (device int32).
+ *   cap_long = E/long_threshold + 1, cap_chunks = 2*E/long_threshold + 2.
+ * workspace: sirgcn_csr_build_workspace_bytes(E, N) bytes of device scratch.
+ */
+size_t sirgcn_csr_build_workspace_bytes(int64_t num_edges, int32_t num_nodes);
+
+typedef struct sirgcn_schedule {
+    int32_t *long_rows;    /* [cap_long]   row id of each long row                        */
+    int32_t *long_first;   /* [cap_long]   first chunk slot of each long row              */
+    int32_t *long_nchunks; /* [cap_long]   number of chunks of each long row              */
+    int32_t *chunk_lrow;   /* [cap_chunks] index into long_rows for each chunk            */
+    int32_t *chunk_beg;    /* [cap_chunks] first edge position of each chunk              */
+} sirgcn_schedule;
+
+int sirgcn_csr_build(const int32_t *src, const int32_t *dst, int64_t num_edges, int32_t num_nodes,
+                     int32_t *indptr_in, int32_t *col_src, int32_t *eid_in,
+                     int32_t *indptr_out, int32_t *row_dst, int32_t *eid_out,
+                     float *in_norm, float *out_norm, float *inv_in_deg,
+                     int32_t long_threshold,
+                     const sirgcn_schedule *sched_in, const sirgcn_schedule *sched_out,
+                     int32_t *counts /* [4] device */,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* Schedule only (graph already in CSR form, e.g. generated on device): fills one
+ * sirgcn_schedule and counts[0..1] = {n_long, n_chunks}. */
+int sirgcn_schedule_build(const int32_t *indptr, int32_t num_rows, int32_t long_threshold,
+                          const sirgcn_schedule *sched, int32_t *counts /* [2] device */, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused edge stage.  Replaces graph.update_all(message_func, fn.sum|mean) and its
+ * autograd backward (conv.py:43-47, :63) for the elementwise
+ * activations; the |E| x d edge tensor is never materialised.
+ *
+ * One sirgcn_edge_args describes one walk over a compressed-row structure:
+ *   rows      = destinations (CSR walk: forward, backward-dQ) or sources (CSC walk: backward-dK)
+ *   idx[p]    = the other endpoint of the edge stored at position p
+ *   eid[p]    = original edge id of position p (only needed when `e` / `de` is given)
+ * Tables (dtype `dtype`): q [*, ldq], k [*, ldk], da [*, lda], e [E, lde] (optional, may be NULL),
+ * out [n_rows, ldo] and de [E, ldde] (optional; backward-dQ only).
+ * dst_scale / src_scale: optional fp32 per-node coefficients (NULL = 1):
+ *   sum: none; mean: dst_scale = inv_in_deg; sym: dst_scale = in_norm, src_scale = out_norm.
+ * They are indexed by the destination / source node id as seen by this walk, i.e. by the
+ * row id or by idx[p] depending on the direction (so callers of a partitioned graph pass
+ * pointers already offset to their local row range for the "row" side).
+ */
+typedef struct sirgcn_edge_args {
+    int32_t n_rows;
+    int32_t d;              /* hidden size (columns that carry data)                     */
+    int32_t dtype;          /* SIRGCN_F32 / BF16 / F16                                   */
+    int32_t act;            /* SIRGCN_ACT_*                                              */
+    float act_param;        /* LeakyReLU negative slope                                  */
+    int32_t long_threshold; /* rows with degree > this are handled via the schedule      */
+    const int32_t *indptr;  /* [n_rows + 1]                                              */
+    const int32_t *idx;     /* [E]                                                       */
+    const int32_t *eid;     /* [E] or NULL                                               */
+    const void *q;  int64_t ldq;
+    const void *k;  int64_t ldk;
+    const void *da; int64_t lda;    /* backward only                                      */
+    const void *e;  int64_t lde;    /* optional projected edge term, indexed by edge id   */
+    void *out;      int64_t ldo;
+    void *de;       int64_t ldde;   /* optional, backward-dQ only: gradient of e          */
+    const float *dst_scale;
+    const float *src_scale;
+    /* long-row schedule of THIS walk (host-known counts; both 0 => no long rows) */
+    sirgcn_schedule sched;
+    int32_t n_long;
+    int32_t n_chunks;
+    float *partial;         /* [n_chunks, ldp] fp32 scratch, ldp = 16B-vectors*elems     */
+} sirgcn_edge_args;
+
+/* bytes of fp32 scratch needed for `partial` */
+size_t sirgcn_edge_partial_bytes(int32_t n_chunks, int32_t d, int32_t dtype);
+
+/* A[u] = dst_scale[u] * sum_{p in row u} src_scale[idx[p]] * act(q[u] + k[idx[p]] + e[eid[p]])   (CSR walk) */
+int sirgcn_edge_fwd(const sirgcn_edge_args *args, void *stream);
+/* dQ[u] = sum_p c_p * dA[u] (*) act'(z_p);  optionally dE[eid[p]] = that summand                  (CSR walk) */
+int sirgcn_edge_bwd_q(const sirgcn_edge_args *args, void *stream);
+/* dK[v] = sum_{p in row v} c_p * dA[idx[p]] (*) act'(q[idx[p]] + k[v] + e[eid[p]])                (CSC walk) */
+int sirgcn_edge_bwd_k(const sirgcn_edge_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Split path for arbitrary (non-elementwise) σ, agg_type 'max'/'min', and the
+ * SIRConvBase/SIREConvBase classes (conv.py:47, :137-221; dictionary-lookup/model.py:17).
+ * Edge tensors here ARE materialised, in CSR position order.
+ */
+/* z[p] = a[asel[p]] (+ b[bsel[p]]) (+ c[csel[p]]) for every edge position p < num_pos.
+ * With (asel, bsel, csel) = (dst of position, src of position, edge id of position) this is the
+ * pre-activation q[dst] + k[src] + e of conv.py:45/:111; with b = c = NULL it is a plain row gather
+ * (edges.dst[...] / edges.src[...] of SIRConvBase, conv.py:158). No alignment requirements. */
+int sirgcn_gather_add(int64_t num_pos, const int32_t *asel, const int32_t *bsel, const int32_t *csel,
+                      const void *a, int64_t lda, const void *b, int64_t ldb, const void *c, int64_t ldc,
+                      void *z, int64_t ldz, int32_t d, int32_t dtype, void *stream);
+/* out[u] = dst_scale[u] * sum_{p in row u} src_scale[idx[p]] * m[pos(p)], summed in position order;
+ * pos(p) = p when perm == NULL else perm[p] (CSC-ordered reduction of a CSR-ordered edge tensor).
+ * Replaces fn.sum / fn.mean (conv.py:41,63) and the index_add_ backward of the gathers (K11). */
+int sirgcn_segment_sum(int32_t n_rows, const int32_t *indptr, const int32_t *idx, const int32_t *perm,
+                       const void *m, int64_t ldm, void *out, int64_t ldo, int32_t d, int32_t dtype,
+                       const float *dst_scale, const float *src_scale, void *stream);
+/* out[u,c] = max/min_{p in row u} m[p,c] (0 for empty rows, as DGL's fn.max), arg[u,c] = winning
+ * position (first extremum in position order) or -1.  Replaces fn.max/fn.min (conv.py:41,47). */
+int sirgcn_segment_minmax(int32_t n_rows, const int32_t *indptr, const void *m, int64_t ldm,
+                          void *out, int64_t ldo, int32_t *arg, int64_t ldarg, int32_t d, int32_t dtype,
+                          int32_t is_min, void *stream);
+/* dm[p,c] = (arg[rsel[p],c] == p) ? dout[rsel[p],c] : 0, rsel[p] = row of position p */
+int sirgcn_segment_minmax_bwd(int64_t num_pos, const int32_t *rsel, const void *dout, int64_t lddo,
+                              const int32_t *arg, int64_t ldarg, void *dm, int64_t lddm,
+                              int32_t d, int32_t dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIRGCN_H_ */

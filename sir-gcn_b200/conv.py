@@ -1,0 +1,165 @@
+"""B200-native SIR-GCN layers — drop-in for /root/reference/models/conv.py.
+
+Same constructors, sub-module names (=> identical ``state_dict``) and ``forward(graph, feat[, efeat])``
+as the reference ``SIRConv`` (conv.py:7-67), ``SIREConv`` (:70-134), ``SIRConvBase`` (:137-177) and
+``SIREConvBase`` (:180-221).  ``graph`` may be this package's ``Graph`` or a ``DGLGraph``.
+
+Data flow of one call (sum / mean / sym, σ ∈ {ReLU, LeakyReLU, GELU(erf), Identity}):
+
+    [Q | K] = feat · [W_Q ; W_K]^T + [b_Q | 0]        one concatenated GEMM      (conv.py:60-61)
+    A       = EdgeAggregate(graph, Q, K, E)            fused CUDA edge stage      (conv.py:43-47,:63)
+    out     = A · W_R^T + b_R                          GEMM                       (conv.py:65)
+
+Any other σ (an arbitrary callable, e.g. Sequential(ReLU, Linear, ReLU)), ``agg_type`` max/min and
+the *Base layers go through the split path GatherAdd -> callable -> SegmentReduce.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+from .function import EdgeAggregate, GatherAdd, SegmentReduce, _pad_cols
+from .gemm import linear as _linear
+from .graph import as_graph
+
+_SUM_LIKE = ("sum", "mean", "sym")
+_AGG_TYPES = ("sum", "mean", "sym", "max", "min")   # what getattr(dgl.function, agg_type) admits (conv.py:41)
+
+
+def classify_activation(act):
+    """(code, param) when σ is an elementwise activation the fused kernels implement, else None."""
+    if isinstance(act, nn.ReLU) or act in (torch.relu, F.relu):
+        return _lib.ACT_RELU, 0.0
+    if isinstance(act, nn.LeakyReLU):
+        return _lib.ACT_LEAKY_RELU, float(act.negative_slope)
+    if isinstance(act, nn.GELU) and act.approximate == "none":
+        return _lib.ACT_GELU, 0.0
+    if isinstance(act, nn.Identity):
+        return _lib.ACT_IDENTITY, 0.0
+    return None
+
+
+def _check_agg(agg_type):
+    if agg_type not in _AGG_TYPES:
+        raise AttributeError(f"module 'dgl.function' has no attribute '{agg_type}'")
+
+
+class SIRConv(nn.Module):
+    r"""h*_u = Σ_{v∈N(u)} W_R σ(W_Q h_u + W_K h_v)   (reference: models/conv.py:7-67)"""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, activation, dropout=0, inner_bias=True,
+                 outer_bias=True, agg_type="sum"):
+        super().__init__()
+        _check_agg(agg_type)
+        self.activation = activation
+        self.dropout = nn.Dropout(dropout)
+        self.linear_query = nn.Linear(input_dim, hidden_dim, bias=inner_bias)
+        self.linear_key = nn.Linear(input_dim, hidden_dim, bias=False)
+        self.linear_relation = nn.Linear(hidden_dim, output_dim, bias=outer_bias)
+        self._agg_type = agg_type
+
+    # -- projections -------------------------------------------------------------------------
+    def _project_qk(self, feat):
+        """K then Q (dropout RNG order of conv.py:60-61) from ONE concatenated GEMM."""
+        lq, lk = self.linear_query, self.linear_key
+        plain = (type(lq) is nn.Linear and type(lk) is nn.Linear and lk.bias is None
+                 and lq.weight.shape == lk.weight.shape)
+        if not plain:
+            k = self.dropout(lk(feat))
+            return self.dropout(lq(feat)), k
+        d = lq.weight.shape[0]
+        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else feat.dtype
+        ldp = _pad_cols(d, dt)
+        wq, wk = lq.weight, lk.weight
+        bq = lq.bias if lq.bias is not None else wq.new_zeros(d)
+        if ldp != d:   # odd hidden sizes (75, 95, ...): zero rows keep every table row 16-B aligned
+            zw, zb = wq.new_zeros(ldp - d, wq.shape[1]), wq.new_zeros(ldp - d)
+            w = torch.cat([wq, zw, wk, zw])
+            b = torch.cat([bq, zb, wq.new_zeros(ldp)])
+        else:
+            w = torch.cat([wq, wk])
+            b = torch.cat([bq, wq.new_zeros(d)])
+        qk = _linear(feat, w, b)
+        q, k = qk[:, :d], qk[:, ldp:ldp + d]
+        q._sirgcn_padded = k._sirgcn_padded = True
+        k = self.dropout(k)
+        q = self.dropout(q)
+        return q, k
+
+    def _edge_term(self, graph, efeat):
+        return None
+
+    def forward(self, graph, feat, efeat=None):
+        g = as_graph(graph)
+        if feat.dim() < 2:
+            raise ValueError("feat must be [N, ..., input_dim]")
+        if feat.shape[0] != g.num_nodes():
+            raise ValueError(f"feat has {feat.shape[0]} rows but the graph has {g.num_nodes()} nodes")
+        n, inner = feat.shape[0], tuple(feat.shape[1:-1])   # conv.py:55 tolerates [N, ..., d_in]
+        q, k = self._project_qk(feat.reshape(-1, feat.shape[-1]))
+        e = self._edge_term(g, efeat)
+        agg = self._agg_type
+        known = classify_activation(self.activation)
+        if agg in _SUM_LIKE and known is not None and not inner:
+            a = EdgeAggregate.apply(q, k, e, g, agg, known[0], known[1])
+            if type(self.linear_relation) is nn.Linear:
+                return _linear(a, self.linear_relation.weight, self.linear_relation.bias)
+            return self.linear_relation(a)
+        # split path: materialise z in CSR order, run the callable, reduce.  Every op of the edge
+        # stage acts per trailing column, so inner dims are folded into the column axis.
+        E = g.num_edges()
+        z = GatherAdd.apply(q.reshape(n, -1), k.reshape(n, -1), e, g)
+        s = self.activation(z.reshape((E,) + inner + (-1,)))
+        if agg in _SUM_LIKE:
+            a = SegmentReduce.apply(s.reshape(E, -1), g, agg)
+            return self.linear_relation(a.reshape((n,) + inner + (-1,)))
+        m = self.linear_relation(s)                     # conv.py:47 — W_R per edge, then max/min
+        out = SegmentReduce.apply(m.reshape(E, -1), g, agg)
+        return out.reshape((n,) + inner + (-1,))
+
+
+class SIREConv(SIRConv):
+    r"""h*_u = Σ_v W_R σ(W_Q h_u + W_E h_uv + W_K h_v)   (reference: models/conv.py:70-134).
+    ``linear_edge`` may be replaced after construction (e.g. nn.Embedding,
+    benchmark-datasets/zinc/model.py:12-15); whatever it is, it is called on ``efeat``."""
+
+    def __init__(self, input_dim, edge_dim, hidden_dim, output_dim, activation, dropout=0, inner_bias=True,
+                 outer_bias=True, agg_type="sum"):
+        super().__init__(input_dim, hidden_dim, output_dim, activation, dropout, inner_bias, outer_bias, agg_type)
+        self.linear_edge = nn.Linear(edge_dim, hidden_dim, bias=False)
+
+    def _edge_term(self, graph, efeat):
+        if efeat.shape[0] != graph.num_edges():
+            raise ValueError(f"efeat has {efeat.shape[0]} rows but the graph has {graph.num_edges()} edges")
+        return self.dropout(self.linear_edge(efeat))    # conv.py:128 (third dropout draw)
+
+    def forward(self, graph, nfeat, efeat):
+        return super().forward(graph, nfeat, efeat)
+
+
+class SIRConvBase(nn.Module):
+    r"""h*_u = Σ_v g([h_u ‖ h_v])   (reference: models/conv.py:137-177)"""
+
+    def __init__(self, message_func, agg_type="sum"):
+        super().__init__()
+        _check_agg(agg_type)
+        self._agg_type = agg_type
+        self._message_func = message_func
+
+    def forward(self, graph, feat, efeat=None):
+        g = as_graph(graph)
+        parts = [GatherAdd.apply(feat, None, None, g), GatherAdd.apply(None, feat, None, g)]
+        if efeat is not None:
+            parts.append(GatherAdd.apply(None, None, efeat, g))
+        m = self._message_func(torch.cat(parts, dim=-1))
+        return SegmentReduce.apply(m, g, self._agg_type)
+
+
+class SIREConvBase(SIRConvBase):
+    r"""h*_u = Σ_v g([h_u ‖ h_uv ‖ h_v])   (reference: models/conv.py:180-221; note the reference
+    concatenates in the order dst, src, edge — conv.py:199)"""
+
+    def forward(self, graph, nfeat, efeat):
+        return super().forward(graph, nfeat, efeat)

@@ -1,0 +1,230 @@
+// Graph index construction on the GPU: COO -> destination-major CSR + source-major CSC (stable),
+// degree norms and the long-row schedule.  Replaces DGL's format conversion and degree queries
+// (/root/reference/models/conv.py:51-52 in_degrees/out_degrees, :63 update_all over the in-CSR).
+// The stable LSD radix sort is cub::DeviceRadixSort (ships with the CUDA toolkit); everything
+// else is hand-written.  Bit-exact against oracle/csr_ref.c and torch.sort(stable=True).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace sirgcn {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+constexpr int kThreads = 256;
+inline unsigned blocks_for(int64_t n, int per_block = kThreads) {
+    return (unsigned)((n + per_block - 1) / per_block);
+}
+
+__global__ void iota_copy_kernel(const int32_t *__restrict__ key_in, int32_t *__restrict__ key_out,
+                                 int32_t *__restrict__ val_out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        key_out[i] = key_in[i];
+        val_out[i] = (int32_t)i;
+    }
+}
+
+// indptr[v] = first position whose key is >= v, from the sorted key array (run boundaries).
+__global__ void indptr_from_sorted_kernel(const int32_t *__restrict__ keys, int64_t n, int32_t num_nodes,
+                                          int32_t *__restrict__ indptr) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t prev = i == 0 ? -1 : keys[i - 1];
+        const int32_t cur = i == n ? num_nodes : keys[i];
+        for (int32_t v = prev + 1; v <= cur; ++v) indptr[v] = (int32_t)i;
+    }
+}
+
+__global__ void empty_indptr_kernel(int32_t *indptr, int32_t num_nodes) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= num_nodes; i += gridDim.x * blockDim.x) indptr[i] = 0;
+}
+
+__global__ void gather_i32_kernel(const int32_t *__restrict__ table, const int32_t *__restrict__ sel,
+                                  int32_t *__restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = table[sel[i]];
+}
+
+__global__ void copy_i32_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = in[i];
+}
+
+__global__ void norms_kernel(const int32_t *__restrict__ indptr_in, const int32_t *__restrict__ indptr_out,
+                             int32_t num_nodes, float *in_norm, float *out_norm, float *inv_in_deg) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < num_nodes; v += gridDim.x * blockDim.x) {
+        const float di = (float)max(indptr_in[v + 1] - indptr_in[v], 1);
+        const float dq = (float)max(indptr_out[v + 1] - indptr_out[v], 1);
+        // IEEE sqrt and division: identical to the CPU oracle's 1.0f / sqrtf(x)
+        if (in_norm) in_norm[v] = __fdiv_rn(1.f, __fsqrt_rn(di));
+        if (out_norm) out_norm[v] = __fdiv_rn(1.f, __fsqrt_rn(dq));
+        if (inv_in_deg) inv_in_deg[v] = __fdiv_rn(1.f, di);
+    }
+}
+
+// Rows with degree > thr are "long": split into ceil(deg/thr) chunks.  Slots are claimed with
+// integer atomics; slot numbering does not influence any floating-point result because each
+// row's partials are always summed in chunk order.
+__global__ void schedule_kernel(const int32_t *__restrict__ indptr, int32_t num_rows, int32_t thr,
+                                sirgcn_schedule s, int32_t *counts /* {n_long, n_chunks} */) {
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < num_rows; row += gridDim.x * blockDim.x) {
+        const int beg = indptr[row];
+        const int deg = indptr[row + 1] - beg;
+        if (deg <= thr) continue;
+        const int nch = (deg + thr - 1) / thr;
+        const int l = atomicAdd(&counts[0], 1);
+        const int first = atomicAdd(&counts[1], nch);
+        s.long_rows[l] = row;
+        s.long_first[l] = first;
+        s.long_nchunks[l] = nch;
+        for (int ch = 0; ch < nch; ++ch) {
+            s.chunk_lrow[first + ch] = l;
+            s.chunk_beg[first + ch] = beg + ch * thr;
+        }
+    }
+}
+
+struct SortScratch {
+    int32_t *keys[2];
+    int32_t *vals[2];
+    void *cub_tmp;
+    size_t cub_bytes;
+};
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+size_t cub_temp_bytes(int64_t E, int end_bit) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<int32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, E, 0, end_bit);
+    return bytes;
+}
+
+int key_bits(int32_t num_nodes) {
+    int b = 1;
+    while (b < 31 && (1LL << b) < (long long)num_nodes) ++b;
+    return b;
+}
+
+// sort (key, edge id) pairs; write indptr, the "other endpoint" array and (optionally) edge ids
+int build_one(const int32_t *key, const int32_t *other, int64_t E, int32_t N, int32_t *indptr,
+              int32_t *other_sorted, int32_t *eid_sorted, SortScratch &ws, cudaStream_t st) {
+    if (E == 0) {
+        empty_indptr_kernel<<<blocks_for(N + 1), kThreads, 0, st>>>(indptr, N);
+        SIRGCN_LAUNCHED();
+        return SIRGCN_OK;
+    }
+    const unsigned grid = std::min(blocks_for(E), (unsigned)kNumSMs * 16);
+    iota_copy_kernel<<<grid, kThreads, 0, st>>>(key, ws.keys[0], ws.vals[0], E);
+    SIRGCN_LAUNCHED();
+    cub::DoubleBuffer<int32_t> k(ws.keys[0], ws.keys[1]), v(ws.vals[0], ws.vals[1]);
+    size_t bytes = ws.cub_bytes;
+    SIRGCN_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp, bytes, k, v, E, 0, key_bits(N), st));
+    g_launches.fetch_add(1);
+    indptr_from_sorted_kernel<<<grid, kThreads, 0, st>>>(k.Current(), E, N, indptr);
+    SIRGCN_LAUNCHED();
+    gather_i32_kernel<<<grid, kThreads, 0, st>>>(other, v.Current(), other_sorted, E);
+    SIRGCN_LAUNCHED();
+    if (eid_sorted) {
+        copy_i32_kernel<<<grid, kThreads, 0, st>>>(v.Current(), eid_sorted, E);
+        SIRGCN_LAUNCHED();
+    }
+    return SIRGCN_OK;
+}
+
+int check_sched(const sirgcn_schedule *s) {
+    SIRGCN_CHECK_ARG(s && s->long_rows && s->long_first && s->long_nchunks && s->chunk_lrow && s->chunk_beg,
+                     "schedule arrays missing");
+    return SIRGCN_OK;
+}
+
+}  // namespace
+}  // namespace sirgcn
+
+extern "C" {
+
+const char *sirgcn_last_error(void) { return sirgcn::g_err; }
+int sirgcn_abi_version(void) { return SIRGCN_ABI_VERSION; }
+uint64_t sirgcn_launch_count(void) { return sirgcn::g_launches.load(); }
+
+size_t sirgcn_csr_build_workspace_bytes(int64_t num_edges, int32_t num_nodes) {
+    using namespace sirgcn;
+    if (num_edges <= 0) return 256;
+    const size_t arr = align_up((size_t)num_edges * sizeof(int32_t));
+    return 4 * arr + align_up(cub_temp_bytes(num_edges, key_bits(num_nodes))) + 256;
+}
+
+int sirgcn_schedule_build(const int32_t *indptr, int32_t num_rows, int32_t long_threshold,
+                          const sirgcn_schedule *sched, int32_t *counts, void *stream) {
+    using namespace sirgcn;
+    SIRGCN_CHECK_ARG(indptr && counts, "indptr/counts is NULL");
+    SIRGCN_CHECK_ARG(long_threshold >= 32, "long_threshold must be >= 32");
+    int rc = check_sched(sched);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SIRGCN_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), st));
+    if (num_rows > 0) {
+        schedule_kernel<<<std::min(blocks_for(num_rows), (unsigned)kNumSMs * 16), kThreads, 0, st>>>(
+            indptr, num_rows, long_threshold, *sched, counts);
+        SIRGCN_LAUNCHED();
+    }
+    return SIRGCN_OK;
+}
+
+int sirgcn_csr_build(const int32_t *src, const int32_t *dst, int64_t num_edges, int32_t num_nodes,
+                     int32_t *indptr_in, int32_t *col_src, int32_t *eid_in,
+                     int32_t *indptr_out, int32_t *row_dst, int32_t *eid_out,
+                     float *in_norm, float *out_norm, float *inv_in_deg,
+                     int32_t long_threshold, const sirgcn_schedule *sched_in, const sirgcn_schedule *sched_out,
+                     int32_t *counts, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace sirgcn;
+    SIRGCN_CHECK_ARG(num_edges >= 0 && num_edges < (1LL << 31), "num_edges=%lld out of int32 range", (long long)num_edges);
+    SIRGCN_CHECK_ARG(num_nodes >= 0, "num_nodes < 0");
+    SIRGCN_CHECK_ARG(indptr_in && indptr_out, "indptr outputs are NULL");
+    SIRGCN_CHECK_ARG(num_edges == 0 || (src && dst && col_src && row_dst), "edge arrays are NULL");
+    const size_t need = sirgcn_csr_build_workspace_bytes(num_edges, num_nodes);
+    if (workspace_bytes < need || (!workspace && num_edges > 0)) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+        return SIRGCN_ENOSPC;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    SortScratch ws{};
+    if (num_edges > 0) {
+        const size_t arr = align_up((size_t)num_edges * sizeof(int32_t));
+        char *base = reinterpret_cast<char *>(workspace);
+        ws.keys[0] = reinterpret_cast<int32_t *>(base);
+        ws.keys[1] = reinterpret_cast<int32_t *>(base + arr);
+        ws.vals[0] = reinterpret_cast<int32_t *>(base + 2 * arr);
+        ws.vals[1] = reinterpret_cast<int32_t *>(base + 3 * arr);
+        ws.cub_tmp = base + 4 * arr;
+        ws.cub_bytes = workspace_bytes - 4 * arr;
+    }
+    int rc = build_one(dst, src, num_edges, num_nodes, indptr_in, col_src, eid_in, ws, st);
+    if (rc) return rc;
+    rc = build_one(src, dst, num_edges, num_nodes, indptr_out, row_dst, eid_out, ws, st);
+    if (rc) return rc;
+    if ((in_norm || out_norm || inv_in_deg) && num_nodes > 0) {
+        norms_kernel<<<std::min(blocks_for(num_nodes), (unsigned)kNumSMs * 16), kThreads, 0, st>>>(
+            indptr_in, indptr_out, num_nodes, in_norm, out_norm, inv_in_deg);
+        SIRGCN_LAUNCHED();
+    }
+    if (counts) {
+        rc = sirgcn_schedule_build(indptr_in, num_nodes, long_threshold, sched_in, counts, stream);
+        if (rc) return rc;
+        rc = sirgcn_schedule_build(indptr_out, num_nodes, long_threshold, sched_out, counts + 2, stream);
+        if (rc) return rc;
+    }
+    return SIRGCN_OK;
+}
+
+}  // extern "C"

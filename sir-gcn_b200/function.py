@@ -1,0 +1,279 @@
+"""torch.autograd.Function wrappers around the C-ABI edge kernels.
+
+``EdgeAggregate`` is the fused replacement of ``graph.update_all(message_func, fn.sum|mean)`` and
+its autograd backward (/root/reference/models/conv.py:43-47,:63): it saves Q, K (and the caller's
+projected edge term) — never an |E| x d tensor — and recomputes the pre-activation in backward.
+``GatherAdd`` / ``SegmentReduce`` form the split path for arbitrary σ, max/min and the *Base layers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .graph import CompressedRows, Graph
+
+
+def _pad_cols(d, dtype):
+    """columns of a 16-byte aligned row holding d elements"""
+    per = 16 // torch.empty((), dtype=dtype).element_size()
+    return (d + per - 1) // per * per
+
+
+def _alloc_table(n, d, dtype, device, zero=False):
+    """[n, d] view of a row-padded buffer (rows 16-B aligned)."""
+    ld = _pad_cols(d, dtype)
+    buf = (torch.zeros if zero else torch.empty)((n, ld), dtype=dtype, device=device)
+    return buf[:, :d]
+
+
+def _table_ok(t):
+    es = t.element_size()
+    if t.dim() != 2 or t.stride(1) != 1 or t.data_ptr() % 16:
+        return False
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), _pad_cols(t.shape[1], t.dtype))
+    if (ld * es) % 16 or ld < _pad_cols(t.shape[1], t.dtype):
+        return False
+    # columns d..pad must be readable zeros: only guaranteed for buffers made by _alloc_table /
+    # the padded GEMM, which is the case when the row is already a whole number of 16-B vectors
+    return (t.shape[1] * es) % 16 == 0 or getattr(t, "_sirgcn_padded", False)
+
+
+def as_table(t):
+    """Return a tensor the kernels can read as a table (16-B aligned rows, zero padding)."""
+    if _table_ok(t):
+        return t
+    out = _alloc_table(t.shape[0], t.shape[1], t.dtype, t.device, zero=True)
+    out.copy_(t)
+    out._sirgcn_padded = True
+    return out
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else _pad_cols(t.shape[1], t.dtype)
+
+
+def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da, e, out, de,
+               dst_scale, src_scale):
+    a = _lib.EdgeArgs()
+    a.n_rows, a.d, a.dtype, a.act = rows.n_rows, d, _lib.DTYPE_CODE[dtype], act
+    a.act_param, a.long_threshold = float(act_param), rows.long_threshold
+    a.indptr, a.idx = rows.indptr.data_ptr(), rows.idx.data_ptr()
+    a.eid = None if rows.eid is None else rows.eid.data_ptr()
+    a.q, a.ldq = q.data_ptr(), _ld(q)
+    a.k, a.ldk = k.data_ptr(), _ld(k)
+    if da is not None:
+        a.da, a.lda = da.data_ptr(), _ld(da)
+    if e is not None:
+        a.e, a.lde = e.data_ptr(), _ld(e)
+    a.out, a.ldo = out.data_ptr(), _ld(out)
+    if de is not None:
+        a.de, a.ldde = de.data_ptr(), _ld(de)
+    a.dst_scale = None if dst_scale is None else dst_scale.data_ptr()
+    a.src_scale = None if src_scale is None else src_scale.data_ptr()
+    a.sched, a.n_long, a.n_chunks = rows.sched, rows.n_long, rows.n_chunks
+    partial = rows.partial(d, dtype)
+    a.partial = None if partial is None else partial.data_ptr()
+    dev = rows.indptr.device
+    with torch.cuda.device(dev):
+        rc = getattr(_lib.lib(), fn_name)(C.byref(a), _lib.stream_ptr(dev))
+    _lib.check(rc, fn_name)
+
+
+def edge_forward(csr: CompressedRows, q, k, e, dst_scale, src_scale, act, act_param):
+    """A = fused edge stage over the rows of `csr` (q indexed by row, k by csr.idx)."""
+    d = q.shape[1]
+    out = _alloc_table(csr.n_rows, d, q.dtype, q.device)
+    if csr.n_rows:
+        _edge_call("sirgcn_edge_fwd", csr, d, q.dtype, act, act_param, q, k, None, e, out, None,
+                   dst_scale, src_scale)
+    out._sirgcn_padded = True
+    return out
+
+
+def edge_backward_q(csr, q, k, e, da, dst_scale, src_scale, act, act_param, want_de):
+    d = q.shape[1]
+    dq = _alloc_table(csr.n_rows, d, q.dtype, q.device)
+    de = _alloc_table(e.shape[0], d, q.dtype, q.device) if (want_de and e is not None) else None
+    if csr.n_rows:
+        _edge_call("sirgcn_edge_bwd_q", csr, d, q.dtype, act, act_param, q, k, da, e, dq, de,
+                   dst_scale, src_scale)
+    return dq, de
+
+
+def edge_backward_k(csc, q, k, e, da, dst_scale, src_scale, act, act_param):
+    d = k.shape[1]
+    dk = _alloc_table(csc.n_rows, d, k.dtype, k.device)
+    if csc.n_rows:
+        _edge_call("sirgcn_edge_bwd_k", csc, d, k.dtype, act, act_param, q, k, da, e, dk, None,
+                   dst_scale, src_scale)
+    return dk
+
+
+class EdgeAggregate(torch.autograd.Function):
+    """A[u] = c_in[u] * sum_{e=(v->u)} c_out[v] * σ(Q[u] + K[v] + E[e])  with σ applied in registers."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, q, k, e, graph: Graph, agg_type, act, act_param):
+        if not q.is_cuda:
+            raise RuntimeError("SIR-GCN edge kernels need CUDA tensors (no CPU fallback)")
+        if e is not None and graph.csr.eid is None:
+            raise RuntimeError("edge features need a graph built with need_eid=True")
+        if k.dtype != q.dtype or (e is not None and e.dtype != q.dtype):
+            k = k.to(q.dtype)
+            e = None if e is None else e.to(q.dtype)
+        q, k = as_table(q.detach()), as_table(k.detach())
+        e = None if e is None else as_table(e.detach())
+        ds, ss = graph.scales(agg_type)
+        out = edge_forward(graph.csr, q, k, e, ds, ss, act, act_param)
+        ctx.save_for_backward(q, k, e)
+        ctx.graph, ctx.agg_type, ctx.act, ctx.act_param = graph, agg_type, act, act_param
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out):
+        q, k, e = ctx.saved_tensors
+        g = ctx.graph
+        ds, ss = g.scales(ctx.agg_type)
+        da = as_table(grad_out.to(q.dtype))
+        need_q, need_k, need_e = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dq = dk = de = None
+        if need_q or (need_e and e is not None):
+            dq, de = edge_backward_q(g.csr, q, k, e, da, ds, ss, ctx.act, ctx.act_param, need_e)
+        if need_k:
+            dk = edge_backward_k(g.csc, q, k, e, da, ds, ss, ctx.act, ctx.act_param)
+        return dq, dk, de, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# split path
+# ----------------------------------------------------------------------------------------------
+def _gather_add(num_pos, parts, d, dtype, device):
+    """parts: list of (table, selector) with table [*, d] (unit column stride)."""
+    z = torch.empty((num_pos, d), dtype=dtype, device=device)
+    if num_pos == 0:
+        return z
+    parts = parts + [(None, None)] * (3 - len(parts))
+    args = []
+    for _, sel in parts:
+        args.append(_lib.ptr(sel))
+    for t, _ in parts:
+        args += [_lib.ptr(t), C.c_int64(0 if t is None else t.stride(0))]
+    with torch.cuda.device(device):
+        rc = _lib.lib().sirgcn_gather_add(C.c_int64(num_pos), *args, _lib.ptr(z), C.c_int64(d), C.c_int32(d),
+                                          C.c_int32(_lib.DTYPE_CODE[dtype]), _lib.stream_ptr(device))
+    _lib.check(rc, "sirgcn_gather_add")
+    return z
+
+
+def _segment_sum(rows: CompressedRows, perm, m, d, dst_scale, src_scale):
+    out = torch.empty((rows.n_rows, d), dtype=m.dtype, device=m.device)
+    if rows.n_rows == 0:
+        return out
+    with torch.cuda.device(m.device):
+        rc = _lib.lib().sirgcn_segment_sum(
+            C.c_int32(rows.n_rows), _lib.ptr(rows.indptr), _lib.ptr(rows.idx), _lib.ptr(perm),
+            _lib.ptr(m), C.c_int64(m.stride(0)), _lib.ptr(out), C.c_int64(d), C.c_int32(d),
+            C.c_int32(_lib.DTYPE_CODE[m.dtype]), _lib.ptr(dst_scale), _lib.ptr(src_scale), _lib.stream_ptr(m.device))
+    _lib.check(rc, "sirgcn_segment_sum")
+    return out
+
+
+def _rowmajor(t):
+    return t if (t.dim() == 2 and t.stride(1) == 1) else t.contiguous()
+
+
+class GatherAdd(torch.autograd.Function):
+    """z[p] = Q[dst(p)] + K[src(p)] + E[eid(p)] for every CSR position p (any operand may be None)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, q, k, e, graph: Graph):
+        ref = next(t for t in (q, k, e) if t is not None)
+        if not ref.is_cuda:
+            raise RuntimeError("SIR-GCN kernels need CUDA tensors (no CPU fallback)")
+        dtype, d = ref.dtype, ref.shape[1]
+        parts = []
+        if q is not None:
+            parts.append((_rowmajor(q.detach().to(dtype)), graph.pos_dst()))
+        if k is not None:
+            parts.append((_rowmajor(k.detach().to(dtype)), graph.csr.idx))
+        if e is not None:
+            parts.append((_rowmajor(e.detach().to(dtype)), graph.pos_eid()))
+        ctx.graph = graph
+        ctx.has = (q is not None, k is not None, e is not None)
+        return _gather_add(graph.num_edges(), parts, d, dtype, ref.device)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dz):
+        g = ctx.graph
+        dz = _rowmajor(dz)
+        d = dz.shape[1]
+        dq = dk = de = None
+        if ctx.has[0] and ctx.needs_input_grad[0]:
+            dq = _segment_sum(g.csr, None, dz, d, None, None)
+        if ctx.has[1] and ctx.needs_input_grad[1]:
+            dk = _segment_sum(g.csc, g.csc_pos(), dz, d, None, None)
+        if ctx.has[2] and ctx.needs_input_grad[2]:
+            de = torch.empty_like(dz)
+            de[g.pos_eid().long()] = dz
+        return dq, dk, de, None
+
+
+class SegmentReduce(torch.autograd.Function):
+    """DGL builtin reducers over CSR-ordered messages m [E, d] (conv.py:41,63): sum / mean / sym
+    (coefficients folded in) or max / min with argmax bookkeeping (0 for empty rows)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, m, graph: Graph, agg_type):
+        if not m.is_cuda:
+            raise RuntimeError("SIR-GCN kernels need CUDA tensors (no CPU fallback)")
+        m = _rowmajor(m.detach())
+        d = m.shape[1]
+        ctx.graph, ctx.agg_type = graph, agg_type
+        rows = graph.csr
+        if agg_type in ("max", "min"):
+            out = torch.empty((rows.n_rows, d), dtype=m.dtype, device=m.device)
+            arg = torch.empty((rows.n_rows, d), dtype=torch.int32, device=m.device)
+            if rows.n_rows:
+                with torch.cuda.device(m.device):
+                    rc = _lib.lib().sirgcn_segment_minmax(
+                        C.c_int32(rows.n_rows), _lib.ptr(rows.indptr), _lib.ptr(m), C.c_int64(m.stride(0)),
+                        _lib.ptr(out), C.c_int64(d), _lib.ptr(arg), C.c_int64(d), C.c_int32(d),
+                        C.c_int32(_lib.DTYPE_CODE[m.dtype]), C.c_int32(agg_type == "min"), _lib.stream_ptr(m.device))
+                _lib.check(rc, "sirgcn_segment_minmax")
+            ctx.save_for_backward(arg)
+            return out
+        ds, ss = graph.scales(agg_type)
+        return _segment_sum(rows, None, m, d, ds, ss)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        g, agg = ctx.graph, ctx.agg_type
+        dout = _rowmajor(dout)
+        d, E = dout.shape[1], g.num_edges()
+        if agg in ("max", "min"):
+            (arg,) = ctx.saved_tensors
+            dm = torch.empty((E, d), dtype=dout.dtype, device=dout.device)
+            if E:
+                with torch.cuda.device(dout.device):
+                    rc = _lib.lib().sirgcn_segment_minmax_bwd(
+                        C.c_int64(E), _lib.ptr(g.pos_dst()), _lib.ptr(dout), C.c_int64(dout.stride(0)),
+                        _lib.ptr(arg), C.c_int64(d), _lib.ptr(dm), C.c_int64(d), C.c_int32(d),
+                        C.c_int32(_lib.DTYPE_CODE[dout.dtype]), _lib.stream_ptr(dout.device))
+                _lib.check(rc, "sirgcn_segment_minmax_bwd")
+            return dm, None, None
+        dm = _gather_add(E, [(dout, g.pos_dst())], d, dout.dtype, dout.device)
+        ds, ss = g.scales(agg)
+        if ds is not None:
+            coef = ds[g.pos_dst().long()]
+            if ss is not None:
+                coef = coef * ss[g.csr.idx.long()]
+            dm = dm * coef.to(dm.dtype).unsqueeze(1)
+        return dm, None, None

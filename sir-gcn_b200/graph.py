@@ -1,0 +1,206 @@
+"""Graph index structures consumed by the CUDA edge kernels.
+
+The reference hands a ``DGLGraph`` to the layer (/root/reference/models/conv.py:49) and lets DGL
+materialise the in-CSR for ``update_all`` and the degree vectors (conv.py:51-52, :63).  Here a graph
+is converted ONCE into a destination-sorted CSR and a source-sorted CSC of int32 indices (stable:
+ties keep edge-id order) by ``sirgcn_csr_build`` on the GPU, together with the degree norms and the
+long-row schedule; the result is cached on the object.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import torch
+
+from . import _lib
+
+DEFAULT_LONG_THRESHOLD = 512
+
+
+class CompressedRows:
+    """One walkable compressed-row structure (the in-CSR or the out-CSC, or a row slice of one)
+    plus its long-row schedule.  ``idx`` holds the other endpoint of each stored edge, ``eid`` the
+    original edge id (or None)."""
+
+    def __init__(self, indptr, idx, eid, long_threshold=DEFAULT_LONG_THRESHOLD, sched=None, counts=None):
+        self.indptr, self.idx, self.eid = indptr, idx, eid
+        self.n_rows = int(indptr.numel()) - 1
+        self.num_pos = int(idx.numel())
+        self.long_threshold = int(long_threshold)
+        if sched is None:
+            sched, counts = _build_schedule(indptr, self.n_rows, self.num_pos, self.long_threshold)
+        self._sched_tensors = sched
+        self.n_long, self.n_chunks = int(counts[0]), int(counts[1])
+        self.sched = _lib.Schedule(*[_lib.ptr(t).value for t in sched])
+        self._partial = {}
+
+    def partial(self, d, dtype):
+        """fp32 scratch for the long-row partial sums (cached per (d, dtype))."""
+        if self.n_chunks == 0:
+            return None
+        key = (d, dtype)
+        buf = self._partial.get(key)
+        if buf is None:
+            nbytes = _lib.lib().sirgcn_edge_partial_bytes(self.n_chunks, d, _lib.DTYPE_CODE[dtype])
+            buf = torch.empty(nbytes // 4, dtype=torch.float32, device=self.indptr.device)
+            self._partial = {key: buf}
+        return buf
+
+    def slice_rows(self, lo, hi):
+        """Rows [lo, hi) as a stand-alone structure (idx keeps global ids) — used by the
+        destination-row partition (partition.py)."""
+        beg, end = int(self.indptr[lo]), int(self.indptr[hi])
+        indptr = (self.indptr[lo:hi + 1] - beg).contiguous()
+        eid = None if self.eid is None else self.eid[beg:end].contiguous()
+        return CompressedRows(indptr, self.idx[beg:end].contiguous(), eid, self.long_threshold)
+
+
+def _sched_alloc(num_pos, thr, device):
+    cap_long = num_pos // thr + 1
+    cap_chunks = 2 * (num_pos // thr) + 2
+    i32 = lambda n: torch.empty(n, dtype=torch.int32, device=device)
+    return [i32(cap_long), i32(cap_long), i32(cap_long), i32(cap_chunks), i32(cap_chunks)]
+
+
+def _build_schedule(indptr, n_rows, num_pos, thr):
+    dev = indptr.device
+    sched = _sched_alloc(num_pos, thr, dev)
+    counts = torch.zeros(2, dtype=torch.int32, device=dev)
+    s = _lib.Schedule(*[_lib.ptr(t).value for t in sched])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().sirgcn_schedule_build(_lib.ptr(indptr), C.c_int32(n_rows), C.c_int32(thr),
+                                                    C.byref(s), _lib.ptr(counts), _lib.stream_ptr(dev)),
+                   "sirgcn_schedule_build")
+    return sched, counts.tolist()
+
+
+class Graph:
+    """COO edge list src->dst over ``num_nodes`` nodes, converted on construction.
+
+    Attributes: ``csr`` (rows = destinations, idx = sources), ``csc`` (rows = sources, idx =
+    destinations), ``in_norm``/``out_norm`` = clamp(deg,1)^-1/2, ``inv_in_deg`` = 1/clamp(in_deg,1).
+    """
+
+    def __init__(self, src, dst, num_nodes, *, need_eid=True, long_threshold=DEFAULT_LONG_THRESHOLD,
+                 validate=False, keep_coo=True):
+        if not (torch.is_tensor(src) and src.is_cuda):
+            raise RuntimeError("Graph needs CUDA index tensors: the SIR-GCN kernels have no CPU fallback")
+        dev = src.device
+        src = src.to(torch.int32).contiguous()
+        dst = dst.to(device=dev, dtype=torch.int32).contiguous()
+        E, N = int(src.numel()), int(num_nodes)
+        if dst.numel() != E:
+            raise ValueError("src and dst differ in length")
+        if E >= 2 ** 31:
+            raise ValueError("num_edges must be < 2^31 (int32 indices)")
+        if validate and E > 0:
+            lo = min(int(src.min()), int(dst.min()))
+            hi = max(int(src.max()), int(dst.max()))
+            if lo < 0 or hi >= N:
+                raise ValueError(f"node ids out of range [0, {N}): min={lo} max={hi}")
+        self.num_nodes_, self.num_edges_, self.device = N, E, dev
+        thr = int(long_threshold)
+        i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
+        f32 = lambda n: torch.empty(n, dtype=torch.float32, device=dev)
+        indptr_in, col_src, indptr_out, row_dst = i32(N + 1), i32(E), i32(N + 1), i32(E)
+        eid_in = i32(E) if need_eid else None
+        eid_out = i32(E) if need_eid else None
+        self.in_norm, self.out_norm, self.inv_in_deg = f32(N), f32(N), f32(N)
+        sched_in, sched_out = _sched_alloc(E, thr, dev), _sched_alloc(E, thr, dev)
+        s_in = _lib.Schedule(*[_lib.ptr(t).value for t in sched_in])
+        s_out = _lib.Schedule(*[_lib.ptr(t).value for t in sched_out])
+        counts = torch.zeros(4, dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        ws_bytes = L.sirgcn_csr_build_workspace_bytes(E, N)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.sirgcn_csr_build(
+                _lib.ptr(src), _lib.ptr(dst), C.c_int64(E), C.c_int32(N),
+                _lib.ptr(indptr_in), _lib.ptr(col_src), _lib.ptr(eid_in),
+                _lib.ptr(indptr_out), _lib.ptr(row_dst), _lib.ptr(eid_out),
+                _lib.ptr(self.in_norm), _lib.ptr(self.out_norm), _lib.ptr(self.inv_in_deg),
+                C.c_int32(thr), C.byref(s_in), C.byref(s_out), _lib.ptr(counts),
+                _lib.ptr(ws), C.c_size_t(ws_bytes), _lib.stream_ptr(dev))
+        _lib.check(rc, "sirgcn_csr_build")
+        c = counts.tolist()  # the one host sync per graph: sizes of the long-row schedule
+        del ws
+        self.csr = CompressedRows(indptr_in, col_src, eid_in, thr, sched_in, c[0:2])
+        self.csc = CompressedRows(indptr_out, row_dst, eid_out, thr, sched_out, c[2:4])
+        self.src, self.dst = (src, dst) if keep_coo else (None, None)
+        self._lazy = {}
+
+    # --- the slice of the DGLGraph API the layer relies on (conv.py:50-55) ---------------------
+    def num_nodes(self):
+        return self.num_nodes_
+
+    def num_edges(self):
+        return self.num_edges_
+
+    def in_degrees(self):
+        return (self.csr.indptr[1:] - self.csr.indptr[:-1]).long()
+
+    def out_degrees(self):
+        return (self.csc.indptr[1:] - self.csc.indptr[:-1]).long()
+
+    # --- helpers of the split (generic σ / max) path ------------------------------------------
+    def pos_dst(self):
+        """destination node of every CSR position, int32 [E]"""
+        t = self._lazy.get("pos_dst")
+        if t is None:
+            deg = self.csr.indptr[1:] - self.csr.indptr[:-1]
+            t = torch.repeat_interleave(torch.arange(self.num_nodes_, dtype=torch.int32, device=self.device),
+                                        deg.long(), output_size=self.num_edges_)
+            self._lazy["pos_dst"] = t
+        return t
+
+    def pos_eid(self):
+        """edge id of every CSR position, int32 [E]"""
+        if self.csr.eid is None:
+            raise RuntimeError("graph was built with need_eid=False")
+        return self.csr.eid
+
+    def csc_pos(self):
+        """CSR position of the edge stored at every CSC position (int32 [E])"""
+        t = self._lazy.get("csc_pos")
+        if t is None:
+            inv = torch.empty(self.num_edges_, dtype=torch.int32, device=self.device)
+            inv[self.csr.eid.long()] = torch.arange(self.num_edges_, dtype=torch.int32, device=self.device)
+            t = inv[self.csc.eid.long()].contiguous()
+            self._lazy["csc_pos"] = t
+        return t
+
+    def scales(self, agg_type):
+        """(dst_scale, src_scale) fp32 vectors realising the aggregator coefficient c_e of
+        conv.py:45 / fn.mean: sum -> (None, None); mean -> (1/clamp(in_deg,1), None);
+        sym -> (in_deg^-1/2, out_deg^-1/2) with degrees clamped to >= 1 (conv.py:51-57)."""
+        if agg_type == "sym":
+            return self.in_norm, self.out_norm
+        if agg_type == "mean":
+            return self.inv_in_deg, None
+        return None, None
+
+
+_dgl_cache = weakref.WeakKeyDictionary()
+
+
+def as_graph(graph) -> Graph:
+    """Accept the repo's own Graph or (when DGL is installed) a DGLGraph, converted once and
+    cached by object identity; the caller's graph is never mutated (conv.py:50 local_scope)."""
+    if isinstance(graph, Graph):
+        return graph
+    if hasattr(graph, "edges") and hasattr(graph, "num_nodes"):
+        try:
+            cached = _dgl_cache.get(graph)
+        except TypeError:
+            cached = None
+        if cached is not None:
+            return cached
+        src, dst = graph.edges(form="uv", order="eid")
+        g = Graph(src, dst, graph.num_nodes())
+        try:
+            _dgl_cache[graph] = g
+        except TypeError:
+            pass
+        return g
+    raise TypeError(f"unsupported graph type {type(graph)!r}")

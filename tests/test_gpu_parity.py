@@ -1,0 +1,374 @@
+"""Parity of the CUDA path (through the C-ABI of libsirgcn.so) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): index construction bit-exact; fp32 within 1e-5 relative;
+bf16/fp16 within 2e-2 relative, where "relative" is max|a-b| / max|b| over the tensor.
+"""
+import os
+
+import pytest
+import torch
+from torch import nn
+
+import sirgcn_b200  # noqa: F401
+from oracle import csr_ref_c
+from oracle.sirconv_ref import (RefGraph, RefSIRConv, RefSIRConvBase, RefSIREConv, RefSIREConvBase,
+                                _norms, _reduce, csr_csc_ref)
+from sirgcn_b200 import (EdgeAggregate, Graph, SIRConv, SIRConvBase, SIREConv, SIREConvBase, _lib,
+                         classify_activation, synth)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FP32_RTOL, LOWP_RTOL = 1e-5, 2e-2
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "sirconv_golden.pt")
+ACTS = {"relu": nn.ReLU, "leaky": lambda: nn.LeakyReLU(0.2), "gelu": nn.GELU, "identity": nn.Identity}
+
+
+def rel_err(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-20) if b.numel() else 0.0
+
+
+def rand_graph(n, e, seed, hub=None):
+    g = torch.Generator().manual_seed(seed)
+    src, dst = torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)
+    if hub is not None and e:
+        dst[: int(e * 0.4)] = hub          # a long destination row
+        src[int(e * 0.5): int(e * 0.8)] = (hub + 1) % n   # a long source row
+    return src, dst
+
+
+# ---- index construction: bit-exact ----------------------------------------------------------------
+@pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (5, 0, 1), (1, 7, 2), (7, 40, 3), (100, 1000, 4),
+                                      (3, 2000, 5), (5000, 50, 6), (20000, 300000, 7)])
+def test_csr_build_bit_exact(n, e, seed):
+    src, dst = rand_graph(n, e, seed, hub=0 if e > 100 else None)
+    g = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
+    ref = csr_csc_ref(src, dst, n)
+    cref = csr_ref_c(src, dst, n)
+    got = (g.csr.indptr, g.csr.idx, g.csr.eid, g.csc.indptr, g.csc.idx, g.csc.eid)
+    for x, y, z in zip(got, ref[:6], cref[:6]):
+        assert torch.equal(x.cpu(), y) and torch.equal(y, z)
+    assert torch.equal(g.in_norm.cpu(), cref[6]) and torch.equal(g.out_norm.cpu(), cref[7])
+    torch.testing.assert_close(g.inv_in_deg.cpu(), 1.0 / g.in_degrees().cpu().clamp(min=1).float())
+    # long-row schedule: every row longer than the threshold is covered exactly once, in order
+    for rows in (g.csr, g.csc):
+        deg = (rows.indptr[1:] - rows.indptr[:-1]).cpu()
+        long_rows = torch.nonzero(deg > 64).flatten()
+        assert rows.n_long == long_rows.numel()
+        assert rows.n_chunks == int(((deg[long_rows] + 63) // 64).sum())
+        lr, lf, ln, cl, cb = [t.cpu() for t in rows._sched_tensors]
+        assert sorted(lr[: rows.n_long].tolist()) == long_rows.tolist()
+        for i in range(rows.n_long):
+            r, first, nch = int(lr[i]), int(lf[i]), int(ln[i])
+            assert nch == (int(deg[r]) + 63) // 64
+            assert cl[first:first + nch].tolist() == [i] * nch
+            assert cb[first:first + nch].tolist() == [int(rows.indptr[r]) + 64 * c for c in range(nch)]
+
+
+def test_graph_without_edge_ids_and_cpu_rejection():
+    src, dst = rand_graph(50, 400, 1)
+    g = Graph(src.to(DEV), dst.to(DEV), 50, need_eid=False)
+    ref = csr_csc_ref(src, dst, 50)
+    assert g.csr.eid is None and torch.equal(g.csr.idx.cpu(), ref[1]) and torch.equal(g.csc.idx.cpu(), ref[4])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Graph(src, dst, 50)
+    with pytest.raises(ValueError):
+        Graph(torch.tensor([0, 99], device=DEV), torch.tensor([0, 1], device=DEV), 50, validate=True)
+
+
+# ---- fused edge stage on raw tables --------------------------------------------------------------
+def oracle_edge(src, dst, n, q, k, e, agg, act):
+    g = RefGraph(src, dst, n)
+    in_norm, out_norm = _norms(g, agg, q)
+    z = q.index_select(0, g.dst) + k.index_select(0, g.src)
+    if e is not None:
+        z = z + e
+    m = out_norm.index_select(0, g.src) * in_norm.index_select(0, g.dst) * act(z)
+    return _reduce(g, m, agg)
+
+
+@pytest.mark.parametrize("agg", ["sum", "mean", "sym"])
+@pytest.mark.parametrize("act", ["relu", "leaky", "gelu", "identity"])
+@pytest.mark.parametrize("d", [8, 60, 64, 75, 80, 95, 128, 256, 512])
+def test_edge_stage_fp32(agg, act, d):
+    n, e = 300, 2500
+    src, dst = rand_graph(n, e, d, hub=5)
+    torch.manual_seed(d)
+    use_e = d in (64, 75, 256)
+    q = torch.randn(n, d, requires_grad=True)
+    k = torch.randn(n, d, requires_grad=True)
+    ef = torch.randn(e, d, requires_grad=True) if use_e else None
+    ref = oracle_edge(src, dst, n, q, k, ef, agg, ACTS[act]())
+    gout = torch.randn_like(ref)
+    rgrads = torch.autograd.grad(ref, [q, k] + ([ef] if use_e else []), gout)
+
+    g = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
+    assert g.csr.n_chunks > 0 and g.csc.n_chunks > 0
+    qg, kg = q.detach().to(DEV).requires_grad_(True), k.detach().to(DEV).requires_grad_(True)
+    eg = ef.detach().to(DEV).requires_grad_(True) if use_e else None
+    code, param = classify_activation(ACTS[act]())
+    out = EdgeAggregate.apply(qg, kg, eg, g, agg, code, param)
+    grads = torch.autograd.grad(out, [qg, kg] + ([eg] if use_e else []), gout.to(DEV))
+    assert rel_err(out, ref) < FP32_RTOL
+    for a, b in zip(grads, rgrads):
+        assert rel_err(a, b) < FP32_RTOL
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("agg,act,d,use_e", [("sum", "relu", 128, False), ("mean", "leaky", 128, True),
+                                             ("sym", "gelu", 64, True), ("mean", "relu", 520, False),
+                                             ("sum", "leaky", 75, True), ("sym", "leaky", 1024, False)])
+def test_edge_stage_low_precision(dtype, agg, act, d, use_e):
+    n, e = 200, 1500
+    src, dst = rand_graph(n, e, d + 1, hub=2)
+    torch.manual_seed(d)
+    rnd = lambda *s: (0.5 * torch.randn(*s)).to(dtype)
+    q, k = rnd(n, d), rnd(n, d)
+    ef = rnd(e, d) if use_e else None
+    q32, k32 = q.float().requires_grad_(True), k.float().requires_grad_(True)
+    e32 = ef.float().requires_grad_(True) if use_e else None
+    ref = oracle_edge(src, dst, n, q32, k32, e32, agg, ACTS[act]())
+    gout = torch.randn_like(ref).to(dtype)
+    rgrads = torch.autograd.grad(ref, [q32, k32] + ([e32] if use_e else []), gout.float())
+
+    g = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
+    qg, kg = q.to(DEV).requires_grad_(True), k.to(DEV).requires_grad_(True)
+    eg = ef.to(DEV).requires_grad_(True) if use_e else None
+    code, param = classify_activation(ACTS[act]())
+    out = EdgeAggregate.apply(qg, kg, eg, g, agg, code, param)
+    assert out.dtype == dtype
+    grads = torch.autograd.grad(out, [qg, kg] + ([eg] if use_e else []), gout.to(DEV))
+    assert rel_err(out, ref) < LOWP_RTOL
+    for a, b in zip(grads, rgrads):
+        assert a.dtype == dtype and rel_err(a, b) < LOWP_RTOL
+
+
+def test_edge_stage_bitwise_repeatable_and_threshold_independent_shape():
+    n, e, d = 400, 6000, 128
+    src, dst = rand_graph(n, e, 9, hub=7)
+    torch.manual_seed(0)
+    q, k = torch.randn(n, d, device=DEV, requires_grad=True), torch.randn(n, d, device=DEV, requires_grad=True)
+    gout = torch.randn(n, d, device=DEV)
+    runs = []
+    for _ in range(3):
+        g = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=128)
+        out = EdgeAggregate.apply(q, k, None, g, "sym", _lib.ACT_GELU, 0.0)
+        runs.append((out.detach().clone(),) + torch.autograd.grad(out, (q, k), gout))
+    for r in runs[1:]:
+        for a, b in zip(r, runs[0]):
+            assert torch.equal(a, b)            # atomic-free, fixed reduction order
+    g2 = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=4096)      # no long rows at all
+    assert g2.csr.n_chunks == 0
+    out2 = EdgeAggregate.apply(q, k, None, g2, "sym", _lib.ACT_GELU, 0.0)
+    assert rel_err(out2, runs[0][0]) < FP32_RTOL
+
+
+# ---- whole layers --------------------------------------------------------------------------------
+def make_pair(cls_ref, cls_gpu, *args, **kw):
+    torch.manual_seed(0)
+    ref = cls_ref(*args, **kw)
+    gpu = cls_gpu(*args, **kw).to(DEV)
+    gpu.load_state_dict(ref.state_dict())           # identical state_dict keys and shapes
+    assert list(gpu.state_dict().keys()) == list(ref.state_dict().keys())
+    return ref, gpu
+
+
+def run_layer(ref, gpu, src, dst, n, feat, efeat=None, rtol=FP32_RTOL):
+    rg, gg = RefGraph(src, dst, n), Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
+    x = feat.clone().requires_grad_(True)
+    ef = efeat.clone().requires_grad_(True) if efeat is not None and efeat.is_floating_point() else efeat
+    out_r = ref(rg, x, ef) if efeat is not None else ref(rg, x)
+    gout = torch.randn_like(out_r)
+    wrt = [x] + ([ef] if ef is not None and ef.requires_grad else []) + list(ref.parameters())
+    gr = torch.autograd.grad(out_r, wrt, gout, allow_unused=True)
+    xg = feat.to(DEV).requires_grad_(True)
+    eg = efeat.to(DEV) if efeat is not None else None
+    if eg is not None and eg.is_floating_point():
+        eg.requires_grad_(True)
+    out_g = gpu(gg, xg, eg) if efeat is not None else gpu(gg, xg)
+    wrtg = [xg] + ([eg] if eg is not None and eg.requires_grad else []) + list(gpu.parameters())
+    gg_ = torch.autograd.grad(out_g, wrtg, gout.to(DEV), allow_unused=True)
+    assert rel_err(out_g, out_r) < rtol, rel_err(out_g, out_r)
+    for a, b in zip(gg_, gr):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert rel_err(a, b) < rtol, rel_err(a, b)
+    return out_g
+
+
+@pytest.mark.parametrize("agg", ["sum", "mean", "sym", "max", "min"])
+@pytest.mark.parametrize("act", ["relu", "leaky", "gelu"])
+def test_sirconv_layer(agg, act):
+    if agg in ("max", "min") and act == "relu":
+        pytest.skip("exact ties after ReLU: DGL routes the gradient to one arg-max edge, ATen splits it")
+    n, e = 150, 1200
+    src, dst = rand_graph(n, e, 11, hub=3)
+    dst[dst == 9] = 10                               # node 9 has no in-edges: b_R (sum) / 0 (max)
+    ref, gpu = make_pair(RefSIRConv, SIRConv, 24, 64, 40, ACTS[act](), agg_type=agg)
+    out = run_layer(ref, gpu, src, dst, n, torch.randn(n, 24))
+    if agg in ("max", "min"):
+        assert torch.equal(out[9], torch.zeros(40, device=DEV))
+    else:
+        torch.testing.assert_close(out[9], gpu.linear_relation.bias)
+
+
+@pytest.mark.parametrize("agg", ["sum", "sym", "max"])
+@pytest.mark.parametrize("d", [64, 75])
+def test_sireconv_layer(agg, d):
+    n, e = 120, 900
+    src, dst = rand_graph(n, e, 12, hub=1)
+    ref, gpu = make_pair(RefSIREConv, SIREConv, 16, 5, d, 32, nn.LeakyReLU(0.2), agg_type=agg)
+    run_layer(ref, gpu, src, dst, n, torch.randn(n, 16), torch.randn(e, 5))
+
+
+def test_sireconv_with_embedding_edge_term():
+    """benchmark-datasets/zinc/model.py:12-15 replaces linear_edge by nn.Embedding after construction."""
+    src, dst, n, atom, bond = synth.zinc_like(num_graphs=8, seed=3)
+    ref, gpu = make_pair(RefSIREConv, SIREConv, 16, 4, 64, 64, nn.LeakyReLU(0.2, inplace=True), agg_type="sym")
+    torch.manual_seed(1)
+    ref.linear_edge = nn.Embedding(4, 64)
+    gpu.linear_edge = nn.Embedding(4, 64).to(DEV)
+    gpu.load_state_dict(ref.state_dict())
+    run_layer(ref, gpu, src, dst, n, torch.randn(n, 16), bond)
+
+
+def test_generic_activation_and_inner_dims():
+    """σ = Sequential(ReLU, Linear, ReLU) (synthetic-datasets/dictionary-lookup/model.py:17)."""
+    n = 10
+    val, key = torch.arange(n, 2 * n), torch.arange(0, n)
+    src, dst = val.repeat_interleave(n), key.repeat(n)
+    torch.manual_seed(0)
+    sigma = nn.Sequential(nn.ReLU(), nn.Linear(40, 40), nn.ReLU())
+    ref = RefSIRConv(40, 40, 40, sigma, agg_type="sum")
+    import copy
+    gpu = SIRConv(40, 40, 40, copy.deepcopy(sigma), agg_type="sum").to(DEV)
+    gpu.load_state_dict(ref.state_dict())
+    out = run_layer(ref, gpu, src, dst, 2 * n, torch.randn(2 * n, 40))
+    torch.testing.assert_close(out[n:], gpu.linear_relation.bias.expand(n, -1))   # isolated destinations
+    # [N, B, d_in] features (conv.py:55)
+    ref3, gpu3 = make_pair(RefSIRConv, SIRConv, 6, 16, 5, nn.GELU(), agg_type="sym")
+    src, dst = rand_graph(30, 200, 5)
+    run_layer(ref3, gpu3, src, dst, 30, torch.randn(30, 3, 6))
+
+
+def test_base_layers():
+    src, dst = rand_graph(40, 300, 13, hub=2)
+    torch.manual_seed(0)
+    mlp = nn.Sequential(nn.Linear(2 * 12, 20), nn.GELU(), nn.Linear(20, 7))
+    for agg in ("sum", "mean", "sym", "max"):
+        ref, gpu = RefSIRConvBase(mlp, agg), SIRConvBase(__import__("copy").deepcopy(mlp).to(DEV), agg)
+        run_layer(ref, gpu, src, dst, 40, torch.randn(40, 12))
+    mlp_e = nn.Sequential(nn.Linear(2 * 12 + 3, 20), nn.GELU(), nn.Linear(20, 7))
+    ref, gpu = RefSIREConvBase(mlp_e, "sym"), SIREConvBase(__import__("copy").deepcopy(mlp_e).to(DEV), "sym")
+    run_layer(ref, gpu, src, dst, 40, torch.randn(40, 12), torch.randn(300, 3))
+
+
+def test_hetero_edge_count_identity_on_gpu():
+    """exact integer known answer (synthetic-datasets/hetero-edge-count/data.py:21)"""
+    n, c = 64, 6
+    src, dst = rand_graph(n, 1500, 21, hub=4)
+    label = torch.randint(0, c, (n,))
+    layer = SIRConv(c, c, 1, nn.ReLU(inplace=True), inner_bias=False, outer_bias=False).to(DEV)
+    with torch.no_grad():
+        layer.linear_query.weight.copy_(torch.eye(c))
+        layer.linear_key.weight.copy_(-torch.eye(c))
+        layer.linear_relation.weight.fill_(1.0)
+    out = layer(Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64), torch.eye(c)[label].to(DEV))
+    assert out.sum().item() == (label[src] != label[dst]).sum().item()
+
+
+def test_golden_vectors():
+    cases = torch.load(GOLDEN)
+    for c in cases:
+        m = c["meta"]
+        if m["edge_dim"]:
+            layer = SIREConv(m["d_in"], m["edge_dim"], m["d"], m["d_out"], ACTS[m["act"]](), agg_type=m["agg"])
+        else:
+            layer = SIRConv(m["d_in"], m["d"], m["d_out"], ACTS[m["act"]](), agg_type=m["agg"])
+        layer.load_state_dict(c["state"])
+        layer.to(DEV)
+        g = Graph(c["src"].to(DEV), c["dst"].to(DEV), m["n"], long_threshold=32)
+        for x, y in zip((g.csr.indptr, g.csr.idx, g.csr.eid, g.csc.indptr, g.csc.idx, g.csc.eid), c["csr"][:6]):
+            assert torch.equal(x.cpu(), y)
+        feat = c["feat"].to(DEV).requires_grad_(True)
+        ef = c["efeat"].to(DEV).requires_grad_(True) if m["edge_dim"] else None
+        out = layer(g, feat, ef) if m["edge_dim"] else layer(g, feat)
+        assert rel_err(out, c["out"]) < FP32_RTOL, m
+        if m["agg"] == "max" and m["act"] == "relu":
+            continue                                  # tie-splitting differs (see test_sirconv_layer)
+        wrt = [feat] + ([ef] if ef is not None else []) + [p for _, p in layer.named_parameters()]
+        grads = torch.autograd.grad(out, wrt, c["gout"].to(DEV), allow_unused=True)
+        assert rel_err(grads[0], c["dfeat"]) < FP32_RTOL, m
+        if ef is not None:
+            assert rel_err(grads[1], c["defeat"]) < FP32_RTOL, m
+        for (name, _), gr in zip(layer.named_parameters(), grads[(2 if ef is not None else 1):]):
+            if gr is not None and c["dparams"][name].abs().max() > 0:
+                assert rel_err(gr, c["dparams"][name]) < FP32_RTOL, (m, name)
+
+
+# ---- execution contexts the reference scripts rely on -----------------------------------------------
+def test_contexts_no_grad_eval_deterministic_autocast():
+    src, dst = rand_graph(100, 800, 14)
+    g = Graph(src.to(DEV), dst.to(DEV), 100)
+    torch.manual_seed(0)
+    layer = SIRConv(32, 128, 32, nn.GELU(), dropout=0.5, agg_type="sym").to(DEV)
+    x = torch.randn(100, 32, device=DEV)
+    torch.use_deterministic_algorithms(True)         # every reference script sets this (set_seed)
+    try:
+        with torch.no_grad():
+            layer.eval()
+            y1, y2 = layer(g, x), layer(g, x)
+            assert torch.equal(y1, y2) and not y1.requires_grad
+        layer.train()                                  # dropout active: K mask drawn first, then Q
+        torch.manual_seed(5)
+        out = layer(g, x.requires_grad_(True))
+        out.sum().backward()
+        assert x.grad is not None and layer.linear_key.weight.grad is not None
+        torch.manual_seed(5)
+        k_ref = layer.dropout(layer.linear_key(x))
+        q_ref = layer.dropout(layer.linear_query(x))
+        code, param = classify_activation(layer.activation)
+        a = EdgeAggregate.apply(q_ref, k_ref, None, g, "sym", code, param)
+        assert rel_err(layer.linear_relation(a), out) < FP32_RTOL
+    finally:
+        torch.use_deterministic_algorithms(False)
+    layer.eval()
+    with torch.autocast("cuda", dtype=torch.float16):  # heterophilous-datasets/train.py:75-81
+        y16 = layer(g, x)
+    assert y16.dtype == torch.float16
+    assert rel_err(y16, layer(g, x)) < LOWP_RTOL
+    # the caller's graph object is not mutated (conv.py:50 local_scope)
+    assert not hasattr(g, "ndata")
+
+
+# ---- full-size properties (sizes the oracle cannot finish quickly) -----------------------------------
+def test_arxiv_sized_properties():
+    src, dst, n = synth.arxiv_like(seed=0, device=DEV)
+    e, d = src.numel(), 256
+    g = Graph(src, dst, n)
+    assert g.csr.n_chunks > 0                          # hubs present
+    # sortedness + permutation checks of the builder at full size
+    assert bool((g.csr.indptr[1:] >= g.csr.indptr[:-1]).all()) and int(g.csr.indptr[-1]) == e
+    assert torch.equal(dst[g.csr.eid.long()], g.pos_dst().long())
+    assert torch.equal(src[g.csr.eid.long()], g.csr.idx.long())
+    assert torch.equal(src[g.csc.eid.long()], torch.repeat_interleave(torch.arange(n, device=DEV), g.out_degrees()))
+    assert torch.equal(torch.sort(g.csr.eid)[0], torch.arange(e, device=DEV, dtype=torch.int32))
+    torch.manual_seed(0)
+    q = torch.randn(n, d, device=DEV, requires_grad=True)
+    k = torch.randn(n, d, device=DEV, requires_grad=True)
+    s = EdgeAggregate.apply(q, k, None, g, "sum", _lib.ACT_LEAKY_RELU, 0.2)
+    m = EdgeAggregate.apply(q, k, None, g, "mean", _lib.ACT_LEAKY_RELU, 0.2)
+    deg = g.in_degrees().clamp(min=1).unsqueeze(1)
+    assert rel_err(m * deg, s) < FP32_RTOL             # mean = sum / clamp(deg, 1)
+    # identity activation: A = deg*q + segment-sum of k  (checked with torch index_add_)
+    lin = EdgeAggregate.apply(q, k, None, g, "sum", _lib.ACT_IDENTITY, 0.0)
+    ref = g.in_degrees().unsqueeze(1) * q.detach() + torch.zeros(n, d, device=DEV).index_add_(0, dst, k.detach()[src])
+    assert rel_err(lin, ref) < FP32_RTOL
+    # gradient of sum(A) for the identity activation: dQ = in_deg, dK = out_deg (exact integers)
+    dq, dk = torch.autograd.grad(lin.sum(), (q, k))
+    assert torch.equal(dq[:, 0], g.in_degrees().float()) and torch.equal(dk[:, 7], g.out_degrees().float())
+    # duplicating every edge doubles the sum aggregate
+    g2 = Graph(torch.cat([src, src]), torch.cat([dst, dst]), n)
+    s2 = EdgeAggregate.apply(q, k, None, g2, "sum", _lib.ACT_LEAKY_RELU, 0.2)
+    assert rel_err(s2, 2 * s) < FP32_RTOL

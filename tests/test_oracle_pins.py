@@ -1,0 +1,206 @@
+"""Pins of the CPU oracle (oracle/sirconv_ref.py, oracle/csr_ref.c).
+
+The reference has no tests and cannot be imported without DGL ("parity unpinned"),
+so the oracle is pinned by known-answer identities derived from the reference's own data generators
+and by algebraic properties of the layer, plus frozen golden vectors.
+"""
+import os
+
+import pytest
+import torch
+from torch import nn
+
+from oracle import csr_ref_c
+from oracle.sirconv_ref import (RefGraph, RefSIRConv, RefSIRConvBase, RefSIREConv, RefSIREConvBase,
+                                csr_csc_ref)
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "sirconv_golden.pt")
+
+
+def rand_graph(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)
+
+
+# ---- index construction ----------------------------------------------------------------------
+@pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (5, 0, 1), (7, 40, 2), (100, 1000, 3), (3, 200, 4), (1000, 50, 5)])
+def test_csr_c_oracle_matches_stable_sort(n, e, seed):
+    src, dst = rand_graph(n, e, seed)
+    a = csr_csc_ref(src, dst, n)
+    b = csr_ref_c(src, dst, n)
+    for x, y in zip(a[:6], b[:6]):
+        assert torch.equal(x, y)
+    torch.testing.assert_close(a[6], b[6], rtol=1e-6, atol=0)
+    torch.testing.assert_close(a[7], b[7], rtol=1e-6, atol=0)
+
+
+def test_csr_semantics():
+    # edges (by id): 0:2->1  1:0->1  2:2->1 (duplicate)  3:1->1 (self loop)  4:0->3 ; node 4 isolated
+    src = torch.tensor([2, 0, 2, 1, 0])
+    dst = torch.tensor([1, 1, 1, 1, 3])
+    ip_in, col, eid_in, ip_out, row, eid_out, in_norm, out_norm = csr_csc_ref(src, dst, 5)
+    assert ip_in.tolist() == [0, 0, 4, 4, 5, 5]
+    assert col.tolist() == [2, 0, 2, 1, 0] and eid_in.tolist() == [0, 1, 2, 3, 4]     # ties keep edge-id order
+    assert ip_out.tolist() == [0, 2, 3, 5, 5, 5]
+    assert eid_out.tolist() == [1, 4, 3, 0, 2] and row.tolist() == [1, 3, 1, 1, 1]
+    assert in_norm.tolist() == pytest.approx([1, 0.5, 1, 1, 1])
+    assert out_norm.tolist() == pytest.approx([2 ** -0.5, 1, 2 ** -0.5, 1, 1])
+
+
+def test_csr_c_oracle_rejects_out_of_range():
+    with pytest.raises(ValueError):
+        csr_ref_c(torch.tensor([0, 9]), torch.tensor([0, 1]), 3)
+
+
+# ---- known answers from the reference's own data generators -----------------------------------
+def test_hetero_edge_count_identity():
+    """synthetic-datasets/hetero-edge-count/data.py:21: target = #edges whose endpoint labels differ.
+    One-hot features, W_Q = I, W_K = -I, b = 0, σ = ReLU, W_R = 1^T  =>  Σ_u out_u = that count,
+    because relu(onehot(a) - onehot(b)) sums to [a != b].  Multigraph + self loops as dgl.rand_graph."""
+    torch.manual_seed(0)
+    for trial in range(5):
+        n, c = 9 + trial, 4
+        src, dst = rand_graph(n, n * n // 2, 10 + trial)
+        label = torch.randint(0, c, (n,))
+        layer = RefSIRConv(c, c, 1, nn.ReLU(), inner_bias=False, outer_bias=False)
+        with torch.no_grad():
+            layer.linear_query.weight.copy_(torch.eye(c))
+            layer.linear_key.weight.copy_(-torch.eye(c))
+            layer.linear_relation.weight.fill_(1.0)
+        out = layer(RefGraph(src, dst, n), torch.eye(c)[label])
+        expected = (label[src] != label[dst]).sum()
+        assert out.sum().item() == expected.item()
+
+
+def test_dictionary_lookup_isolated_destinations():
+    """synthetic-datasets/dictionary-lookup/data.py:27-31: complete bipartite val->key graph; val nodes
+    have no in-edges => output b_R for sum/mean/sym, 0 for max (DGL zero-fills empty rows)."""
+    n = 6
+    val, key = torch.arange(n, 2 * n), torch.arange(0, n)
+    src = val.repeat_interleave(n)
+    dst = key.repeat(n)
+    g = RefGraph(src, dst, 2 * n)
+    assert g.in_degrees().tolist() == [n] * n + [0] * n
+    feat = torch.randn(2 * n, 5)
+    for agg in ("sum", "mean", "sym"):
+        layer = RefSIRConv(5, 7, 3, nn.ReLU(), agg_type=agg)
+        out = layer(g, feat)
+        assert torch.equal(out[n:], layer.linear_relation.bias.expand(n, -1))
+    out = RefSIRConv(5, 7, 3, nn.ReLU(), agg_type="max")(g, feat)
+    assert torch.equal(out[n:], torch.zeros(n, 3))
+    assert out[:n].abs().sum() > 0
+
+
+# ---- algebraic identities --------------------------------------------------------------------
+def _pair(agg_a, agg_b, act=nn.GELU):
+    torch.manual_seed(1)
+    a = RefSIRConv(6, 8, 4, act(), agg_type=agg_a, outer_bias=False)
+    b = RefSIRConv(6, 8, 4, act(), agg_type=agg_b, outer_bias=False)
+    b.load_state_dict(a.state_dict())
+    return a, b
+
+
+def test_sym_on_regular_graph_is_sum_over_degree():
+    n, k = 12, 3
+    dst = torch.arange(n).repeat_interleave(k)
+    src = (dst + torch.arange(1, k + 1).repeat(n)) % n          # every node: in = out = k
+    g = RefGraph(src, dst, n)
+    a, b = _pair("sym", "sum")
+    x = torch.randn(n, 6)
+    torch.testing.assert_close(a(g, x), b(g, x) / k, rtol=1e-5, atol=1e-6)
+
+
+def test_mean_is_sum_over_clamped_degree():
+    src, dst = rand_graph(15, 60, 3)
+    dst[dst == 4] = 5                                            # node 4: no in-edges
+    g = RefGraph(src, dst, 15)
+    a, b = _pair("mean", "sum")
+    x = torch.randn(15, 6)
+    deg = g.in_degrees().clamp(min=1).unsqueeze(1)
+    torch.testing.assert_close(a(g, x), b(g, x) / deg, rtol=1e-5, atol=1e-6)
+
+
+def test_edge_permutation_invariance_and_duplication():
+    src, dst = rand_graph(20, 90, 4)
+    layer = RefSIREConv(6, 3, 8, 4, nn.LeakyReLU(0.2), outer_bias=False)
+    x, ef = torch.randn(20, 6), torch.randn(90, 3)
+    base = layer(RefGraph(src, dst, 20), x, ef)
+    p = torch.randperm(90)
+    torch.testing.assert_close(layer(RefGraph(src[p], dst[p], 20), x, ef[p]), base, rtol=1e-5, atol=1e-5)
+    dup = layer(RefGraph(torch.cat([src, src]), torch.cat([dst, dst]), 20), x, torch.cat([ef, ef]))
+    torch.testing.assert_close(dup, 2 * base, rtol=1e-5, atol=1e-5)
+
+
+def test_direction_src_to_dst():
+    """eq is read at the destination, ek at the source (conv.py:45); output row = destination."""
+    layer = RefSIRConv(2, 2, 2, nn.Identity(), inner_bias=False, outer_bias=False)
+    with torch.no_grad():
+        layer.linear_query.weight.copy_(torch.eye(2))
+        layer.linear_key.weight.copy_(10 * torch.eye(2))
+        layer.linear_relation.weight.copy_(torch.eye(2))
+    x = torch.tensor([[1.0, 0.0], [0.0, 1.0]])
+    out = layer(RefGraph([0], [1], 2), x)                        # single edge 0 -> 1
+    assert out.tolist() == [[0.0, 0.0], [10.0, 1.0]]             # q(node1) + 10*k(node0) lands on node 1
+
+
+def test_base_layers_match_sirconv():
+    """SIRConvBase with g([h_u‖h_v]) = W_R σ(W_Q h_u + W_K h_v) equals SIRConv (conv.py:137-177 vs 7-67)."""
+    src, dst = rand_graph(11, 50, 6)
+    g = RefGraph(src, dst, 11)
+    conv = RefSIRConv(5, 7, 3, nn.ReLU(), outer_bias=False, agg_type="sym")
+
+    class G(nn.Module):
+        def forward(self, m):
+            hu, hv = m[:, :5], m[:, 5:]
+            return conv.linear_relation(conv.activation(conv.linear_query(hu) + conv.linear_key(hv)))
+    x = torch.randn(11, 5)
+    torch.testing.assert_close(RefSIRConvBase(G(), "sym")(g, x), conv(g, x), rtol=1e-5, atol=1e-5)
+    ef = torch.randn(50, 2)
+    out = RefSIREConvBase(lambda m: m, "sum")(g, x, ef)
+    assert out.shape == (11, 12)
+    torch.testing.assert_close(out[:, 10:], torch.zeros(11, 2).index_add_(0, dst, ef))
+
+
+@pytest.mark.parametrize("agg", ["sum", "mean", "sym", "max"])
+def test_gradcheck_fp64(agg):
+    torch.manual_seed(0)
+    src, dst = rand_graph(6, 14, 7)
+    g = RefGraph(src, dst, 6)
+    layer = RefSIREConv(3, 2, 4, 3, nn.GELU(), agg_type=agg).double()
+    x = torch.randn(6, 3, dtype=torch.double, requires_grad=True)
+    ef = torch.randn(14, 2, dtype=torch.double, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda a, b: layer(g, a, b), (x, ef), eps=1e-6, atol=1e-5)
+
+
+def test_min_and_unknown_aggregators():
+    src, dst = rand_graph(6, 14, 8)
+    g = RefGraph(src, dst, 6)
+    torch.manual_seed(0)
+    mx = RefSIRConv(3, 4, 2, nn.ReLU(), agg_type="max")
+    mn = RefSIRConv(3, 4, 2, nn.ReLU(), agg_type="min")
+    mn.load_state_dict(mx.state_dict())
+    x = torch.randn(6, 3)
+    assert (mn(g, x) <= mx(g, x)).all()
+    with pytest.raises(AttributeError):
+        RefSIRConv(3, 4, 2, nn.ReLU(), agg_type="median")(g, x)
+
+
+# ---- frozen vectors ----------------------------------------------------------------------------
+def test_oracle_reproduces_golden():
+    from tests.golden.make_golden import ACTS
+    cases = torch.load(GOLDEN)
+    assert len(cases) >= 16
+    for c in cases:
+        m = c["meta"]
+        if m["edge_dim"]:
+            layer = RefSIREConv(m["d_in"], m["edge_dim"], m["d"], m["d_out"], ACTS[m["act"]](), agg_type=m["agg"])
+        else:
+            layer = RefSIRConv(m["d_in"], m["d"], m["d_out"], ACTS[m["act"]](), agg_type=m["agg"])
+        layer.load_state_dict(c["state"])
+        feat = c["feat"].clone().requires_grad_(True)
+        out = layer(RefGraph(c["src"], c["dst"], m["n"]), feat, c["efeat"])
+        torch.testing.assert_close(out, c["out"], rtol=1e-6, atol=1e-6)
+        (dfeat,) = torch.autograd.grad(out, feat, c["gout"])
+        torch.testing.assert_close(dfeat, c["dfeat"], rtol=1e-6, atol=1e-6)
+        for x, y in zip(csr_csc_ref(c["src"], c["dst"], m["n"])[:6], c["csr"][:6]):
+            assert torch.equal(x, y)
