@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib
-from .function import EdgeAggregate, GatherAdd, SegmentReduce, _pad_cols
+from .function import EdgeAggregate, GatherAdd, SegmentReduce, SIRLayerFunction, _pad_cols
 from .gemm import linear as _linear
 from .graph import as_graph
 
@@ -59,28 +59,33 @@ class SIRConv(nn.Module):
         self.linear_key = nn.Linear(input_dim, hidden_dim, bias=False)
         self.linear_relation = nn.Linear(hidden_dim, output_dim, bias=outer_bias)
         self._agg_type = agg_type
+        self._agg_func = "sum" if agg_type == "sym" else agg_type   # name of the DGL builtin (conv.py:41)
 
     # -- projections -------------------------------------------------------------------------
+    def _plain(self):
+        lq, lk, lr = self.linear_query, self.linear_key, self.linear_relation
+        return (type(lq) is nn.Linear and type(lk) is nn.Linear and type(lr) is nn.Linear
+                and lk.bias is None and lq.weight.shape == lk.weight.shape)
+
+    def _cat_qk_weights(self, dtype):
+        """[W_Q ; W_K] (+ zero rows so that each half is a whole number of 16-B vectors for odd
+        hidden sizes such as the published 75 / 95) and [b_Q | 0]."""
+        wq, wk, bq = self.linear_query.weight, self.linear_key.weight, self.linear_query.bias
+        d = wq.shape[0]
+        ldp = _pad_cols(d, dtype)
+        bq = bq if bq is not None else wq.new_zeros(d)
+        if ldp != d:
+            zw, zb = wq.new_zeros(ldp - d, wq.shape[1]), wq.new_zeros(ldp - d)
+            return torch.cat([wq, zw, wk, zw]), torch.cat([bq, zb, wq.new_zeros(ldp)]), d, ldp
+        return torch.cat([wq, wk]), torch.cat([bq, wq.new_zeros(d)]), d, ldp
+
     def _project_qk(self, feat):
         """K then Q (dropout RNG order of conv.py:60-61) from ONE concatenated GEMM."""
-        lq, lk = self.linear_query, self.linear_key
-        plain = (type(lq) is nn.Linear and type(lk) is nn.Linear and lk.bias is None
-                 and lq.weight.shape == lk.weight.shape)
-        if not plain:
-            k = self.dropout(lk(feat))
-            return self.dropout(lq(feat)), k
-        d = lq.weight.shape[0]
+        if not self._plain():
+            k = self.dropout(self.linear_key(feat))
+            return self.dropout(self.linear_query(feat)), k
         dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else feat.dtype
-        ldp = _pad_cols(d, dt)
-        wq, wk = lq.weight, lk.weight
-        bq = lq.bias if lq.bias is not None else wq.new_zeros(d)
-        if ldp != d:   # odd hidden sizes (75, 95, ...): zero rows keep every table row 16-B aligned
-            zw, zb = wq.new_zeros(ldp - d, wq.shape[1]), wq.new_zeros(ldp - d)
-            w = torch.cat([wq, zw, wk, zw])
-            b = torch.cat([bq, zb, wq.new_zeros(ldp)])
-        else:
-            w = torch.cat([wq, wk])
-            b = torch.cat([bq, wq.new_zeros(d)])
+        w, b, d, ldp = self._cat_qk_weights(dt)
         qk = _linear(feat, w, b)
         q, k = qk[:, :d], qk[:, ldp:ldp + d]
         q._sirgcn_padded = k._sirgcn_padded = True
@@ -98,10 +103,18 @@ class SIRConv(nn.Module):
         if feat.shape[0] != g.num_nodes():
             raise ValueError(f"feat has {feat.shape[0]} rows but the graph has {g.num_nodes()} nodes")
         n, inner = feat.shape[0], tuple(feat.shape[1:-1])   # conv.py:55 tolerates [N, ..., d_in]
-        q, k = self._project_qk(feat.reshape(-1, feat.shape[-1]))
-        e = self._edge_term(g, efeat)
         agg = self._agg_type
         known = classify_activation(self.activation)
+        dropping = self.training and self.dropout.p > 0
+        if agg in _SUM_LIKE and known is not None and not inner and not dropping and self._plain():
+            # one autograd node for the whole layer (nn.Dropout is the identity here)
+            dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else feat.dtype
+            w, b, d, _ = self._cat_qk_weights(dt)
+            e = self._edge_term(g, efeat)
+            lr = self.linear_relation
+            return SIRLayerFunction.apply(feat, w, b, e, lr.weight, lr.bias, g, agg, known[0], known[1], d)
+        q, k = self._project_qk(feat.reshape(-1, feat.shape[-1]))
+        e = self._edge_term(g, efeat)
         if agg in _SUM_LIKE and known is not None and not inner:
             a = EdgeAggregate.apply(q, k, e, g, agg, known[0], known[1])
             if type(self.linear_relation) is nn.Linear:

@@ -56,6 +56,8 @@ def _ld(t):
 
 def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da, e, out, de,
                dst_scale, src_scale):
+    if not (rows.indptr.is_cuda and q.is_cuda and k.is_cuda and out.is_cuda):
+        raise RuntimeError("SIR-GCN edge kernels need CUDA tensors (no CPU fallback)")
     a = _lib.EdgeArgs()
     a.n_rows, a.d, a.dtype, a.act = rows.n_rows, d, _lib.DTYPE_CODE[dtype], act
     a.act_param, a.long_threshold = float(act_param), rows.long_threshold
@@ -92,9 +94,9 @@ def edge_forward(csr: CompressedRows, q, k, e, dst_scale, src_scale, act, act_pa
     return out
 
 
-def edge_backward_q(csr, q, k, e, da, dst_scale, src_scale, act, act_param, want_de):
+def edge_backward_q(csr, q, k, e, da, dst_scale, src_scale, act, act_param, want_de, out=None):
     d = q.shape[1]
-    dq = _alloc_table(csr.n_rows, d, q.dtype, q.device)
+    dq = _alloc_table(csr.n_rows, d, q.dtype, q.device) if out is None else out
     de = _alloc_table(e.shape[0], d, q.dtype, q.device) if (want_de and e is not None) else None
     if csr.n_rows:
         _edge_call("sirgcn_edge_bwd_q", csr, d, q.dtype, act, act_param, q, k, da, e, dq, de,
@@ -102,9 +104,9 @@ def edge_backward_q(csr, q, k, e, da, dst_scale, src_scale, act, act_param, want
     return dq, de
 
 
-def edge_backward_k(csc, q, k, e, da, dst_scale, src_scale, act, act_param):
+def edge_backward_k(csc, q, k, e, da, dst_scale, src_scale, act, act_param, out=None):
     d = k.shape[1]
-    dk = _alloc_table(csc.n_rows, d, k.dtype, k.device)
+    dk = _alloc_table(csc.n_rows, d, k.dtype, k.device) if out is None else out
     if csc.n_rows:
         _edge_call("sirgcn_edge_bwd_k", csc, d, k.dtype, act, act_param, q, k, da, e, dk, None,
                    dst_scale, src_scale)
@@ -146,6 +148,63 @@ class EdgeAggregate(torch.autograd.Function):
         if need_k:
             dk = edge_backward_k(g.csc, q, k, e, da, ds, ss, ctx.act, ctx.act_param)
         return dq, dk, de, None, None, None, None
+
+
+class SIRLayerFunction(torch.autograd.Function):
+    """One whole SIRConv/SIREConv call for the sum-like aggregators as ONE autograd node
+    (SURVEY.md §8b): [Q|K] = H·W_qk^T + b  ->  fused edge stage  ->  out = A·W_R^T + b_R.
+    Saves H, [Q|K], A (and the caller's projected edge term) — never an |E| x d tensor.  Backward
+    writes dQ and dK straight into the two halves of one [N, 2·ld] buffer so the weight/input
+    gradients of the concatenated projection are single GEMMs, and frees dA before dH is made."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, feat, w_qk, b_qk, e, w_r, b_r, graph, agg_type, act, act_param, d):
+        from . import gemm
+        if not feat.is_cuda:
+            raise RuntimeError("SIR-GCN kernels need CUDA tensors (no CPU fallback)")
+        if e is not None and graph.csr.eid is None:
+            raise RuntimeError("edge features need a graph built with need_eid=True")
+        qk = gemm.linear_forward(feat, w_qk, b_qk)                 # [N, 2*ldp]
+        ldp = qk.shape[1] // 2
+        q, k = qk[:, :d], qk[:, ldp:ldp + d]
+        q._sirgcn_padded = k._sirgcn_padded = True
+        if e is not None:
+            e = as_table(e.detach().to(qk.dtype))
+        ds, ss = graph.scales(agg_type)
+        a = edge_forward(graph.csr, q, k, e, ds, ss, act, act_param)
+        out = gemm.linear_forward(a, w_r, b_r)
+        ctx.save_for_backward(feat, qk, e, a, w_qk, w_r)
+        ctx.graph, ctx.agg_type, ctx.act, ctx.act_param, ctx.d = graph, agg_type, act, act_param, d
+        ctx.has_bias = (b_qk is not None, b_r is not None)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        from . import gemm
+        feat, qk, e, a, w_qk, w_r = ctx.saved_tensors
+        g, d = ctx.graph, ctx.d
+        ldp = qk.shape[1] // 2
+        q, k = qk[:, :d], qk[:, ldp:ldp + d]
+        q._sirgcn_padded = k._sirgcn_padded = True
+        need = ctx.needs_input_grad
+        gout = gout.to(qk.dtype)
+        gout = gout if gout.stride(-1) == 1 else gout.contiguous()
+        dw_r = gemm.linear_wgrad(gout, a, w_r.dtype) if need[4] else None
+        db_r = gout.sum(0).to(w_r.dtype) if (need[5] and ctx.has_bias[1]) else None
+        da = gemm.linear_dgrad(gout, w_r.to(qk.dtype), pad_to=_pad_cols(d, qk.dtype))[:, :d]   # [N, d]
+        da._sirgcn_padded = True
+        ds, ss = g.scales(ctx.agg_type)
+        dqk = (torch.empty if ldp == d else torch.zeros)(qk.shape, dtype=qk.dtype, device=qk.device)
+        dq, dk = dqk[:, :d], dqk[:, ldp:ldp + d]
+        _, de = edge_backward_q(g.csr, q, k, e, da, ds, ss, ctx.act, ctx.act_param, need[3], out=dq)
+        edge_backward_k(g.csc, q, k, e, da, ds, ss, ctx.act, ctx.act_param, out=dk)
+        del da
+        dw_qk = gemm.linear_wgrad(dqk, feat, w_qk.dtype) if need[1] else None
+        db_qk = dqk.sum(0).to(w_qk.dtype) if (need[2] and ctx.has_bias[0]) else None
+        dfeat = gemm.linear_dgrad(dqk, w_qk.to(qk.dtype)).to(feat.dtype) if need[0] else None
+        return dfeat, dw_qk, db_qk, de, dw_r, db_r, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------

@@ -29,7 +29,10 @@ class CompressedRows:
         self.num_pos = int(idx.numel())
         self.long_threshold = int(long_threshold)
         if sched is None:
-            sched, counts = _build_schedule(indptr, self.n_rows, self.num_pos, self.long_threshold)
+            if indptr.is_cuda:
+                sched, counts = _build_schedule(indptr, self.n_rows, self.num_pos, self.long_threshold)
+            else:   # host-side structure (partition planning / gloo tests): never handed to a kernel
+                sched, counts = [torch.empty(0, dtype=torch.int32)] * 5, (0, 0)
         self._sched_tensors = sched
         self.n_long, self.n_chunks = int(counts[0]), int(counts[1])
         self.sched = _lib.Schedule(*[_lib.ptr(t).value for t in sched])
