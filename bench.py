@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py — SIR-GCN conv fwd+bwd throughput (Gedges/s) and fraction of the HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload P|A] [--scale S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on host cores
+
+One "step" = forward + backward of the L SIRConv layers of the workload over the whole synthetic
+graph (BASELINE.json configs[4] "P": power-law graph, 50 M nodes / 2 B edges, d_hidden 128, 2 layers,
+bf16 tables with fp32 accumulation, σ = ReLU, mean aggregation; destination-row partitioned when
+N > 1).  Metric: Gedges/s = E·L / t(step).  `value` is timed with the node features resident in HBM;
+`e2e` times the same step through the layer API with the node features copied from pinned host memory
+and a checksum of the output + the weight gradients read back, every step.
+Inputs (≥ 12.8 GB per table at scale 1) are far larger than the 126 MB L2, so no L2 flush is needed.
+
+The `roofline` object is measured live: CUDA events are recorded around every sirgcn_edge_* C-ABI call
+(on the stream the kernels are launched on) inside the timed region; algorithmic bytes follow
+SURVEY.md §8(d) / DESIGN.md.  `cpu_baseline` is the CPU oracle (a port of the reference's DGL path,
+oracle/sirconv_ref.py) timed on a bounded sample of the same workload on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
+import torch  # noqa: E402
+from torch import nn  # noqa: E402
+
+METRIC = "sirgcn_conv_fwd_bwd_gedges_per_s"
+UNIT = "Gedges/s"
+
+WORKLOADS = {
+    # name: nodes, edges, d_in, d_hidden, layers, dtype, agg, act
+    "P": dict(nodes=50_000_000, edges=2_000_000_000, d_in=128, d=128, layers=2, dtype="bf16", agg="mean",
+              act="relu", max_deg=None, desc="power-law 50M nodes / 2B edges, d=128, 2 layers (BASELINE configs[4])"),
+    "A": dict(nodes=169_343, edges=1_166_243, d_in=128, d=256, layers=3, dtype="f32", agg="sum",
+              act="leaky", max_deg=13_000, desc="ogbn-arxiv-shaped 169,343 nodes / 1.17M edges, 128->256, 3 layers (configs[2])"),
+}
+DTYPES = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}
+
+
+def make_act(name):
+    return {"relu": nn.ReLU(), "leaky": nn.LeakyReLU(0.2), "gelu": nn.GELU()}[name]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def edge_bytes(kind, E, N, r, eps=0):
+    """algorithmic bytes of one edge-stage launch: r = d·sizeof(elem)"""
+    if kind == "sirgcn_edge_fwd":
+        return E * (r + 4 + eps) + N * (2 * r + 4)
+    if kind == "sirgcn_edge_bwd_q":
+        return E * (r + 4 + eps) + N * (3 * r + 4)
+    return E * (2 * r + 4 + eps) + N * (2 * r + 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the oracle port of the reference's DGL path, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_shape(w, target_edges):
+    f = max(1, round(w["edges"] / target_edges))
+    return max(64, w["nodes"] // f), max(64, w["edges"] // f), f
+
+
+def build_cpu_case(w, target_edges):
+    from oracle.sirconv_ref import RefGraph, RefSIRConv
+    from sirgcn_b200 import synth
+    n, e, f = cpu_sample_shape(w, target_edges)
+    src, dst, n = synth.powerlaw(n, e, alpha=2.3, max_deg=w["max_deg"], seed=0, device="cpu", index_dtype=torch.int64)
+    torch.manual_seed(0)
+    dims = [w["d_in"]] + [w["d"]] * w["layers"]
+    layers = [RefSIRConv(dims[i], w["d"], w["d"], make_act(w["act"]), agg_type=w["agg"]) for i in range(w["layers"])]
+    x = torch.randn(n, w["d_in"])
+    gout = torch.randn(n, w["d"])
+    g = RefGraph(src, dst, n)
+
+    def step():
+        h = x.clone().requires_grad_(True)
+        for p in (p for l in layers for p in l.parameters()):
+            p.grad = None
+        out = h
+        for l in layers:
+            out = l(g, out)
+        out.backward(gout)
+        return float(out.detach().sum())
+
+    sample = (f"1/{f} sample of the workload with the same degree law: {n:,} nodes / {e:,} edges, fp32, "
+              f"{w['layers']} layers fwd+bwd, oracle/sirconv_ref.py (index_select / index_add_, the ops DGL lowers to)")
+    return step, e * w["layers"], sample
+
+
+def time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, edges_per_step, sample = build_cpu_case(w, args.cpu_edges)
+    t = time_cpu(step, args.steps, args.warmup)
+    value = edges_per_step / t / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, w),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, w):
+    n, e = scaled_shape(args, w)
+    return {"workload": f"{args.workload}: {w['desc']}" + ("" if args.scale == 1 else f" at scale {args.scale:g}"),
+            "nodes": n, "edges": e, "d_in": w["d_in"], "d_hidden": w["d"], "layers": w["layers"],
+            "agg": w["agg"], "activation": w["act"], "table_dtype": w["dtype"],
+            "partition": "single GPU" if args.gpus == 1 else f"1-D destination rows over {args.gpus} GPUs",
+            "l2": "inputs >> 126 MB L2, no flush" if e * w["d"] * (4 if w["dtype"] == "f32" else 2) > (1 << 30)
+            else "L2 flushed (256 MiB write) between timed steps"}
+
+
+def scaled_shape(args, w):
+    return max(64, int(w["nodes"] * args.scale)), max(64, int(w["edges"] * args.scale))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args, w):
+    import torch.distributed as dist
+    import sirgcn_b200  # noqa: F401  (fails loudly if libsirgcn.so is missing: no CPU fallback)
+    from sirgcn_b200 import Graph, SIRConv, _lib, function, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    dtype = DTYPES[w["dtype"]]
+    n, e = scaled_shape(args, w)
+    L, d = w["layers"], w["d"]
+    torch.manual_seed(0)
+    dims = [w["d_in"]] + [d] * L
+    layers = nn.ModuleList([SIRConv(dims[i], d, d, make_act(w["act"]), agg_type=w["agg"]) for i in range(L)]).to(dev)
+    if world > 1:
+        for p in layers.parameters():
+            dist.broadcast(p.data, 0)
+    params = list(layers.parameters())
+
+    # ---- graph + features -------------------------------------------------------------------
+    t_build = time.perf_counter()
+    if world == 1:
+        src, dst, n = synth.powerlaw(n, e, alpha=2.3, max_deg=w["max_deg"], seed=0, device=dev)
+        graph = Graph(src, dst, n, need_eid=False, keep_coo=False)
+        del src, dst
+        n_local, e_local = n, e
+        run_layer = lambda layer, h: layer(graph, h)
+    else:
+        from sirgcn_b200 import partition
+        part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, alpha=2.3, max_deg=w["max_deg"],
+                                                         seed=0, device=dev)
+        n_local, e_local = part.n_local, part.num_local_edges
+        run_layer = lambda layer, h: partition.partitioned_sirconv(layer, part, h)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    x_dev = torch.empty((n_local, w["d_in"]), dtype=dtype, device=dev)
+    chunk = 1 << 22
+    for lo in range(0, n_local, chunk):   # bounded fp32 temporaries
+        hi = min(n_local, lo + chunk)
+        x_dev[lo:hi] = torch.randn((hi - lo, w["d_in"]), generator=gen, device=dev).to(dtype)
+    gout = torch.empty((n_local, d), dtype=dtype, device=dev)
+    for lo in range(0, n_local, chunk):
+        hi = min(n_local, lo + chunk)
+        gout[lo:hi] = torch.randn((hi - lo, d), generator=gen, device=dev).to(dtype)
+    x_dev.requires_grad_(True)
+
+    def step(x):
+        x.grad = None
+        for p in params:
+            p.grad = None
+        h = x
+        for layer in layers:
+            h = run_layer(layer, h)
+        check = h.detach().sum(dtype=torch.float32)
+        h.backward(gout)
+        return check
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    small = e * d * torch.empty((), dtype=dtype).element_size() <= (1 << 30)
+    flush_buf = torch.empty(1 << 28, dtype=torch.uint8, device=dev) if small else None   # 256 MiB > 126 MB L2
+
+    def timed(fn, steps):
+        """K steps between barriers; each step bracketed by CUDA events on the launching stream (the L2
+        flush of small workloads sits between the brackets); returns the max over ranks of ms/step"""
+        barrier()
+        evs = []
+        for _ in range(steps):
+            if flush_buf is not None:
+                flush_buf.fill_(1)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            fn()
+            t1.record()
+            evs.append((t0, t1))
+        barrier()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------
+    for _ in range(args.warmup):
+        step(x_dev)
+    sampler = ClockSampler(local) if rank == 0 else None
+    function.EDGE_TIMERS = []
+    launches0 = _lib.launch_count()
+    ms_step = timed(lambda: step(x_dev), args.steps)
+    launches = _lib.launch_count() - launches0
+    timers, function.EDGE_TIMERS = function.EDGE_TIMERS, None
+    clocks = sampler.stop() if sampler else None
+    peak_mem = torch.cuda.max_memory_allocated() / 2**30
+
+    # per-kernel durations (CUDA events around each C-ABI edge call, inside the timed region)
+    per = {}
+    for name, t0, t1, rows in timers:
+        acc = per.setdefault(name, [0.0, 0, 0, 0])
+        acc[0] += t0.elapsed_time(t1)
+        acc[1] += 1
+        acc[2], acc[3] = rows.num_pos, rows.n_rows
+    es = torch.empty((), dtype=dtype).element_size()
+    peak, peak_src = peaks()
+    stages = {}
+    for name, (ms, cnt, epos, nrows) in per.items():
+        by = edge_bytes(name, epos, nrows, d * es)
+        avg = ms / cnt
+        stages[name] = {"ms": avg, "bytes": by, "gbs": by / avg / 1e6, "frac": by / avg / 1e6 / peak,
+                        "share_of_step": ms / (ms_step * args.steps)}
+    dom = max(stages, key=lambda k: stages[k]["ms"]) if stages else None
+    tot_ms = sum(s["ms"] for s in stages.values())
+    tot_by = sum(s["bytes"] for s in stages.values())
+
+    # ---- e2e: node features from pinned host memory, results read back, every step -----------------
+    x_dev.grad = None
+    x_host = torch.empty((n_local, w["d_in"]), dtype=dtype, pin_memory=True)
+    x_host.copy_(x_dev.detach())
+    d2h = [0]
+
+    def e2e_step():
+        with torch.no_grad():
+            x_dev.copy_(x_host, non_blocking=True)      # this step's inputs: pinned host -> HBM
+        check = step(x_dev)
+        outs = [check.cpu()] + [p.grad.cpu() for p in params]   # results back on the host
+        d2h[0] = sum(t.numel() * t.element_size() for t in outs)
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, max(1, min(args.steps, 3)))
+    h2d = x_host.numel() * x_host.element_size()
+
+    # ---- CPU baseline on rank 0 (bounded sample) --------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del x_host
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cstep, cedges, sample = build_cpu_case(w, args.cpu_edges)
+        t = time_cpu(cstep, 2, 1)
+        cpu = {"value": cedges / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        total_edges = e * L
+        line = {
+            "metric": METRIC, "value": total_edges / (ms_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": workload_config(args, w),
+            "e2e": {"value": total_edges / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
+                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h[0] * world,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": None if dom is None else {
+                "bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": stages[dom]["gbs"] / 8000.0,
+                "edge_stage_total": {"ms": tot_ms, "bytes": tot_by, "gbs": tot_by / tot_ms / 1e6,
+                                     "frac": tot_by / tot_ms / 1e6 / peak,
+                                     "share_of_step": sum(v[0] for v in per.values()) / (ms_step * args.steps)},
+                "stages": stages},
+            "cpu_baseline": cpu,
+            "graph_build_s": t_build, "peak_mem_gib": peak_mem,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="P", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's nodes/edges (debug)")
+    ap.add_argument("--cpu-edges", type=int, default=4_000_000, help="edges of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_gpu(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -60,6 +60,7 @@ class SIRConv(nn.Module):
         self.linear_relation = nn.Linear(hidden_dim, output_dim, bias=outer_bias)
         self._agg_type = agg_type
         self._agg_func = "sum" if agg_type == "sym" else agg_type   # name of the DGL builtin (conv.py:41)
+        self.recompute_qk = None    # None = auto (see forward); not part of the reference surface
 
     # -- projections -------------------------------------------------------------------------
     def _plain(self):
@@ -112,7 +113,11 @@ class SIRConv(nn.Module):
             w, b, d, _ = self._cat_qk_weights(dt)
             e = self._edge_term(g, efeat)
             lr = self.linear_relation
-            return SIRLayerFunction.apply(feat, w, b, e, lr.weight, lr.bias, g, agg, known[0], known[1], d)
+            recompute = self.recompute_qk
+            if recompute is None:     # auto: do not keep a projection larger than 4 GiB for backward
+                recompute = 2 * n * _pad_cols(d, dt) * torch.empty((), dtype=dt).element_size() > (1 << 32)
+            return SIRLayerFunction.apply(feat, w, b, e, lr.weight, lr.bias, g, agg, known[0], known[1], d,
+                                          bool(recompute))
         q, k = self._project_qk(feat.reshape(-1, feat.shape[-1]))
         e = self._edge_term(g, efeat)
         if agg in _SUM_LIKE and known is not None and not inner:

@@ -54,6 +54,11 @@ def _ld(t):
     return t.stride(0) if t.shape[0] > 1 else _pad_cols(t.shape[1], t.dtype)
 
 
+# bench.py sets this to a list to collect (entry point, start event, end event, rows) of every edge
+# call, recorded on the stream the kernels are launched on (roofline measurement); None = off
+EDGE_TIMERS = None
+
+
 def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da, e, out, de,
                dst_scale, src_scale):
     if not (rows.indptr.is_cuda and q.is_cuda and k.is_cuda and out.is_cuda):
@@ -61,7 +66,9 @@ def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da
     a = _lib.EdgeArgs()
     a.n_rows, a.d, a.dtype, a.act = rows.n_rows, d, _lib.DTYPE_CODE[dtype], act
     a.act_param, a.long_threshold = float(act_param), rows.long_threshold
-    a.indptr, a.idx = rows.indptr.data_ptr(), rows.idx.data_ptr()
+    # an edgeless graph has an empty idx tensor (NULL data_ptr): hand the kernels any valid address,
+    # it is never dereferenced because every row is empty
+    a.indptr, a.idx = rows.indptr.data_ptr(), (rows.idx.data_ptr() or rows.indptr.data_ptr())
     a.eid = None if rows.eid is None else rows.eid.data_ptr()
     a.q, a.ldq = q.data_ptr(), _ld(q)
     a.k, a.ldk = k.data_ptr(), _ld(k)
@@ -79,7 +86,13 @@ def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da
     a.partial = None if partial is None else partial.data_ptr()
     dev = rows.indptr.device
     with torch.cuda.device(dev):
+        if EDGE_TIMERS is not None:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
         rc = getattr(_lib.lib(), fn_name)(C.byref(a), _lib.stream_ptr(dev))
+        if EDGE_TIMERS is not None:
+            t1.record()
+            EDGE_TIMERS.append((fn_name, t0, t1, rows))
     _lib.check(rc, fn_name)
 
 
@@ -159,7 +172,7 @@ class SIRLayerFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
-    def forward(ctx, feat, w_qk, b_qk, e, w_r, b_r, graph, agg_type, act, act_param, d):
+    def forward(ctx, feat, w_qk, b_qk, e, w_r, b_r, graph, agg_type, act, act_param, d, recompute_qk=False):
         from . import gemm
         if not feat.is_cuda:
             raise RuntimeError("SIR-GCN kernels need CUDA tensors (no CPU fallback)")
@@ -173,8 +186,13 @@ class SIRLayerFunction(torch.autograd.Function):
             e = as_table(e.detach().to(qk.dtype))
         ds, ss = graph.scales(agg_type)
         a = edge_forward(graph.csr, q, k, e, ds, ss, act, act_param)
+        # recompute_qk: the [N, 2d] projection is not kept for backward but re-made from `feat` by one
+        # more GEMM (≈5 % of the edge stage) — on the 50 M-node graph that is 25.6 GB per layer
+        if recompute_qk:
+            del q, k
+            qk = None
         out = gemm.linear_forward(a, w_r, b_r)
-        ctx.save_for_backward(feat, qk, e, a, w_qk, w_r)
+        ctx.save_for_backward(feat, qk, e, a, w_qk, w_r, b_qk if recompute_qk else None)
         ctx.graph, ctx.agg_type, ctx.act, ctx.act_param, ctx.d = graph, agg_type, act, act_param, d
         ctx.has_bias = (b_qk is not None, b_r is not None)
         return out
@@ -183,8 +201,10 @@ class SIRLayerFunction(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gout):
         from . import gemm
-        feat, qk, e, a, w_qk, w_r = ctx.saved_tensors
+        feat, qk, e, a, w_qk, w_r, b_qk = ctx.saved_tensors
         g, d = ctx.graph, ctx.d
+        if qk is None:
+            qk = gemm.linear_forward(feat, w_qk, b_qk)
         ldp = qk.shape[1] // 2
         q, k = qk[:, :d], qk[:, ldp:ldp + d]
         q._sirgcn_padded = k._sirgcn_padded = True
@@ -204,7 +224,7 @@ class SIRLayerFunction(torch.autograd.Function):
         dw_qk = gemm.linear_wgrad(dqk, feat, w_qk.dtype) if need[1] else None
         db_qk = dqk.sum(0).to(w_qk.dtype) if (need[2] and ctx.has_bias[0]) else None
         dfeat = gemm.linear_dgrad(dqk, w_qk.to(qk.dtype)).to(feat.dtype) if need[0] else None
-        return dfeat, dw_qk, db_qk, de, dw_r, db_r, None, None, None, None, None
+        return dfeat, dw_qk, db_qk, de, dw_r, db_r, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
