@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIRGCN_ABI_VERSION 1
+#define SIRGCN_ABI_VERSION 3
 
 /* element types of feature tables (accumulation is always fp32) */
 enum { SIRGCN_F32 = 0, SIRGCN_BF16 = 1, SIRGCN_F16 = 2 };
@@ -89,6 +89,20 @@ int sirgcn_csr_build(const int32_t *src, const int32_t *dst, int64_t num_edges, 
 int sirgcn_schedule_build(const int32_t *indptr, int32_t num_rows, int32_t long_threshold,
                           const sirgcn_schedule *sched, int32_t *counts /* [2] device */, void *stream);
 
+/* Work tiles: rows are grouped so that every tile holds about SIRGCN_TILE_WORK work units, one
+ * unit per stored edge plus SIRGCN_ROW_COST per row (the q read / A write of a row costs about as
+ * much as a few gathered neighbours), whatever the degree distribution.  With
+ * w(r) = indptr[r] + SIRGCN_ROW_COST * r, tile t holds the rows with floor(w(r)/SIRGCN_TILE_WORK) == t:
+ *   tile_row[t] = min { r : w(r) >= t * SIRGCN_TILE_WORK },   tile_row[n_tiles] = num_rows,
+ *   n_tiles = sirgcn_num_tiles(num_rows, num_edges) = (num_edges + ROW_COST*num_rows) / TILE_WORK + 1.
+ * A tile never holds more than TILE_WORK / ROW_COST = 128 rows.  Purely a function of indptr, so
+ * the decomposition — and with it every floating-point summation order — is reproducible. */
+#define SIRGCN_TILE_WORK 512
+#define SIRGCN_ROW_COST 4
+int64_t sirgcn_num_tiles(int32_t num_rows, int64_t num_edges);
+int sirgcn_tiles_build(const int32_t *indptr, int32_t num_rows, int64_t num_edges,
+                       int32_t *tile_row /* [n_tiles + 1] */, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * Fused edge stage.  Replaces graph.update_all(message_func, fn.sum|mean) and its
  * autograd backward (conv.py:43-47, :63) for the elementwise
@@ -122,6 +136,9 @@ typedef struct sirgcn_edge_args {
     const void *e;  int64_t lde;    /* optional projected edge term, indexed by edge id   */
     void *out;      int64_t ldo;
     void *de;       int64_t ldde;   /* optional, backward-dQ only: gradient of e          */
+    void *da_scaled; int64_t ldds;  /* optional, backward-dQ only: dA[u] * dst_scale[u] per row, so that the
+                                       CSC walk can gather an already scaled table (then called with
+                                       da = da_scaled, dst_scale = NULL); may alias `da` (in place)      */
     const float *dst_scale;
     const float *src_scale;
     /* long-row schedule of THIS walk (host-known counts; both 0 => no long rows) */
@@ -129,6 +146,9 @@ typedef struct sirgcn_edge_args {
     int32_t n_long;
     int32_t n_chunks;
     float *partial;         /* [n_chunks, ldp] fp32 scratch, ldp = 16B-vectors*elems     */
+    /* work tiles of THIS walk (sirgcn_tiles_build): tile t = rows [tile_row[t], tile_row[t+1]) */
+    const int32_t *tile_row; /* [n_tiles + 1]                                            */
+    int32_t n_tiles;
 } sirgcn_edge_args;
 
 /* bytes of fp32 scratch needed for `partial` */

@@ -19,6 +19,7 @@ DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 EXPORTS = (
     "sirgcn_last_error", "sirgcn_abi_version", "sirgcn_launch_count",
     "sirgcn_csr_build_workspace_bytes", "sirgcn_csr_build", "sirgcn_schedule_build",
+    "sirgcn_num_tiles", "sirgcn_tiles_build",
     "sirgcn_edge_partial_bytes", "sirgcn_edge_fwd", "sirgcn_edge_bwd_q", "sirgcn_edge_bwd_k",
     "sirgcn_gather_add", "sirgcn_segment_sum", "sirgcn_segment_minmax", "sirgcn_segment_minmax_bwd",
 )
@@ -40,9 +41,11 @@ class EdgeArgs(C.Structure):
         ("e", C.c_void_p), ("lde", C.c_int64),
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("de", C.c_void_p), ("ldde", C.c_int64),
+        ("da_scaled", C.c_void_p), ("ldds", C.c_int64),
         ("dst_scale", C.c_void_p), ("src_scale", C.c_void_p),
         ("sched", Schedule), ("n_long", C.c_int32), ("n_chunks", C.c_int32),
         ("partial", C.c_void_p),
+        ("tile_row", C.c_void_p), ("n_tiles", C.c_int32),
     ]
 
 
@@ -62,6 +65,8 @@ def lib():
         l.sirgcn_launch_count.restype = C.c_uint64
         l.sirgcn_csr_build_workspace_bytes.restype = C.c_size_t
         l.sirgcn_csr_build_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+        l.sirgcn_num_tiles.restype = C.c_int64
+        l.sirgcn_num_tiles.argtypes = [C.c_int32, C.c_int64]
         l.sirgcn_edge_partial_bytes.restype = C.c_size_t
         l.sirgcn_edge_partial_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         _lib = l

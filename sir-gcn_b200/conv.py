@@ -89,9 +89,13 @@ class SIRConv(nn.Module):
         w, b, d, ldp = self._cat_qk_weights(dt)
         qk = _linear(feat, w, b)
         q, k = qk[:, :d], qk[:, ldp:ldp + d]
-        q._sirgcn_padded = k._sirgcn_padded = True
-        k = self.dropout(k)
-        q = self.dropout(q)
+        if self.training and self.dropout.p > 0:
+            # nn.Dropout draws its mask per memory layout: on contiguous [N, d] tensors the K and Q masks
+            # are bit-identical to the reference's two separate projections (K drawn first, conv.py:60-61)
+            k = self.dropout(k.contiguous())
+            q = self.dropout(q.contiguous())
+        else:
+            q._sirgcn_padded = k._sirgcn_padded = True
         return q, k
 
     def _edge_term(self, graph, efeat):

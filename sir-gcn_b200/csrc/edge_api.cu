@@ -3,10 +3,15 @@
 
 namespace sirgcn {
 enum Mode { kFwd = 0, kBwdQ = 1, kBwdK = 2 };
-template <typename T> int edge_launch(const sirgcn_edge_args &a, int mode, cudaStream_t st);
-extern template int edge_launch<float>(const sirgcn_edge_args &, int, cudaStream_t);
-extern template int edge_launch<__nv_bfloat16>(const sirgcn_edge_args &, int, cudaStream_t);
-extern template int edge_launch<__half>(const sirgcn_edge_args &, int, cudaStream_t);
+template <typename T, int MODE> int edge_launch(const sirgcn_edge_args &a, cudaStream_t st);
+#define SIRGCN_DECL(T)                                                                  \
+    extern template int edge_launch<T, kFwd>(const sirgcn_edge_args &, cudaStream_t);   \
+    extern template int edge_launch<T, kBwdQ>(const sirgcn_edge_args &, cudaStream_t);  \
+    extern template int edge_launch<T, kBwdK>(const sirgcn_edge_args &, cudaStream_t);
+SIRGCN_DECL(float)
+SIRGCN_DECL(__nv_bfloat16)
+SIRGCN_DECL(__half)
+#undef SIRGCN_DECL
 
 namespace {
 
@@ -36,8 +41,12 @@ int validate(const sirgcn_edge_args *a, int mode) {
         SIRGCN_CHECK_ARG(a->eid != nullptr, "dE requested without edge ids");
         SIRGCN_CHECK_ARG(aligned16(a->de) && a->ldde >= ldmin && (a->ldde * es) % 16 == 0, "bad dE table");
     }
+    if (mode == kBwdQ && a->da_scaled) {
+        SIRGCN_CHECK_ARG(aligned16(a->da_scaled) && a->ldds >= ldmin && (a->ldds * es) % 16 == 0, "bad scaled-dA table");
+    }
     SIRGCN_CHECK_ARG(a->n_chunks >= 0 && a->n_long >= 0 && ((a->n_chunks == 0) == (a->n_long == 0)),
                      "inconsistent schedule counts");
+    SIRGCN_CHECK_ARG(a->n_tiles >= 0 && (a->n_tiles == 0 || a->tile_row), "work tiles missing (sirgcn_tiles_build)");
     if (a->n_chunks > 0) {
         SIRGCN_CHECK_ARG(a->partial && aligned16(a->partial), "partial scratch missing / misaligned");
         SIRGCN_CHECK_ARG(a->sched.long_rows && a->sched.long_first && a->sched.long_nchunks &&
@@ -51,11 +60,18 @@ int dispatch(const sirgcn_edge_args *a, int mode, void *stream) {
     int rc = validate(a, mode);
     if (rc != SIRGCN_OK || a->n_rows == 0) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    switch (a->dtype) {
-        case SIRGCN_F32: return edge_launch<float>(*a, mode, st);
-        case SIRGCN_BF16: return edge_launch<__nv_bfloat16>(*a, mode, st);
-        default: return edge_launch<__half>(*a, mode, st);
+#define SIRGCN_MODE(T)                                             \
+    switch (mode) {                                                \
+        case kFwd: return edge_launch<T, kFwd>(*a, st);            \
+        case kBwdQ: return edge_launch<T, kBwdQ>(*a, st);          \
+        default: return edge_launch<T, kBwdK>(*a, st);             \
     }
+    switch (a->dtype) {
+        case SIRGCN_F32: SIRGCN_MODE(float)
+        case SIRGCN_BF16: SIRGCN_MODE(__nv_bfloat16)
+        default: SIRGCN_MODE(__half)
+    }
+#undef SIRGCN_MODE
 }
 
 }  // namespace

@@ -1,0 +1,5 @@
+// Instantiation of the fused edge kernels: __half tables, kBwdK walk (see edge_kernels.cuh).
+#include "edge_kernels.cuh"
+namespace sirgcn {
+template int edge_launch<__half, kBwdK>(const sirgcn_edge_args &, cudaStream_t);
+}

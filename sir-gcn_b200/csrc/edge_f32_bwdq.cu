@@ -1,0 +1,5 @@
+// Instantiation of the fused edge kernels: float tables, kBwdQ walk (see edge_kernels.cuh).
+#include "edge_kernels.cuh"
+namespace sirgcn {
+template int edge_launch<float, kBwdQ>(const sirgcn_edge_args &, cudaStream_t);
+}

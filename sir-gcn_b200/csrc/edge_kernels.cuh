@@ -3,17 +3,21 @@
 // update_all(UDF message, fn.sum/mean) call of /root/reference/models/conv.py:43-47,:63 and its
 // autograd backward.  The |E| x d edge tensor never exists.
 //
-// Work decomposition
-//   * one warp per row; a row's 16-byte feature vectors are spread over G lanes (G = next pow2
-//     of the vector count, <= 32) so a warp gathers 32/G neighbour rows per step with 128-bit
-//     loads; rows wider than 32 vectors keep VPL vectors per lane.
-//   * neighbour ids / edge ids / per-edge coefficients are loaded coalesced (one per lane, 32 per
-//     step) and broadcast with shuffles.
-//   * U independent gathers are in flight per lane before any arithmetic (latency hiding).
-//   * rows longer than `long_threshold` are skipped by the row kernel and processed as
-//     fixed-size chunks (one warp per chunk -> fp32 partial) + an ordered finalize, so hubs of a
-//     power-law graph are spread over the whole chip; every reduction order is fixed
-//     => results are bitwise repeatable, no atomics anywhere.
+// Work decomposition (see DESIGN.md "Edge kernels")
+//   * rows are grouped at graph-build time into TILES of ~512 work units (one unit per edge + 4 per
+//     row), so every warp gets the same amount of work whatever the degree distribution; one warp
+//     walks one tile, row after row.  Rows longer than `long_threshold` are skipped there and
+//     processed as fixed-size CHUNKS (one warp per chunk -> fp32 partial) + an ordered finalize, so
+//     the hubs of a power-law graph are spread over the whole chip.
+//   * a row's 16-byte feature vectors are spread over G lanes (G = next pow2 of the vector count,
+//     <= 32), so a warp gathers 32/G neighbour rows per step with 128-bit requests.
+//   * gathers never touch registers: each lane issues cp.async (LDGSTS, 16 B, L2-only) for exactly
+//     the vectors it will later consume into a per-warp ring of S stages in shared memory, so S
+//     batches of random rows are in flight per warp while it does the arithmetic of the oldest one —
+//     including across row boundaries (the index stream of a tile is contiguous and prefetched two
+//     32-entry windows ahead, the q/dA rows of the next row ride in the same ring).
+//   * every reduction order is fixed (lane-group shuffle tree, chunk order) => results are bitwise
+//     repeatable; there are no atomics anywhere.
 #pragma once
 #include "common.cuh"
 
@@ -21,237 +25,434 @@ namespace sirgcn {
 namespace {
 
 enum Mode { kFwd = 0, kBwdQ = 1, kBwdK = 2 };
+constexpr int kWarps = 8;            // warps per CTA
+constexpr int kTileRowCap = 128;     // max rows per tile = tile_work / row_cost (graph_build.cu)
+constexpr unsigned kFull = 0xffffffffu;
 
-template <int VPL> struct Unroll { static constexpr int U = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1); };
+// cp.async with a 32-bit shared address + immediate offset (no generic->shared conversion per copy)
+template <int OFF> __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0+%2], [%1], 16;" ::"r"(saddr), "l"(gmem), "n"(OFF) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void cp_async4(uint32_t saddr, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0+%2], [%1], 4;" ::"r"(saddr), "l"(gmem), "n"(OFF) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int OFF> __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr), "n"(OFF));
+    return r;
+}
+template <int OFF> __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(r) : "r"(saddr), "n"(OFF));
+    return r;
+}
+template <int OFF> __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(saddr), "r"(v), "n"(OFF) : "memory");
+}
+__device__ __forceinline__ int ldg_idx(const int32_t *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 
-struct WalkCtx {
-    int lane, G, NG, gi, li, nvec;
+// ---- mixed-precision element access: out[i] = c[i] + element i of a 16-byte table vector ---------------
+// sm_100a has fp32 += bf16/fp16 adds that read one half of a packed register (SASS FHADD[.BF16] Rn.H0/H1),
+// so 16-bit tables are consumed without any unpack instructions and z = q + k is exact in fp32.
+template <typename T> __device__ __forceinline__ void add_vec(const uint4 &raw, const float (&c)[VecTraits<T>::N],
+                                                              float (&out)[VecTraits<T>::N]);
+template <> __device__ __forceinline__ void add_vec<float>(const uint4 &raw, const float (&c)[4], float (&out)[4]) {
+    out[0] = c[0] + __uint_as_float(raw.x); out[1] = c[1] + __uint_as_float(raw.y);
+    out[2] = c[2] + __uint_as_float(raw.z); out[3] = c[3] + __uint_as_float(raw.w);
+}
+#define SIRGCN_MIXED_ADD(SUFFIX)                                                                         \
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};                                                  \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) {                                                      \
+        unsigned short lo, hi;                                                                           \
+        asm("mov.b32 {%0,%1}, %2;" : "=h"(lo), "=h"(hi) : "r"(w[i]));                                     \
+        asm("add.rn.f32." SUFFIX " %0, %1, %2;" : "=f"(out[2 * i]) : "h"(lo), "f"(c[2 * i]));             \
+        asm("add.rn.f32." SUFFIX " %0, %1, %2;" : "=f"(out[2 * i + 1]) : "h"(hi), "f"(c[2 * i + 1]));     \
+    }
+template <> __device__ __forceinline__ void add_vec<__nv_bfloat16>(const uint4 &raw, const float (&c)[8], float (&out)[8]) {
+    SIRGCN_MIXED_ADD("bf16")
+}
+template <> __device__ __forceinline__ void add_vec<__half>(const uint4 &raw, const float (&c)[8], float (&out)[8]) {
+    SIRGCN_MIXED_ADD("f16")
+}
+#undef SIRGCN_MIXED_ADD
+
+// ---- activations as compile-time functors (a runtime switch per element costs issue slots) -------------
+template <int ACT> struct Act;
+template <> struct Act<SIRGCN_ACT_RELU> {
+    static __device__ __forceinline__ float f(float z, float) { return fmaxf(z, 0.f); }
+    static __device__ __forceinline__ float d(float z, float) { return z > 0.f ? 1.f : 0.f; }
+};
+template <> struct Act<SIRGCN_ACT_LEAKY_RELU> {      // also serves Identity (slope 1)
+    static __device__ __forceinline__ float f(float z, float p) { return z > 0.f ? z : p * z; }
+    static __device__ __forceinline__ float d(float z, float p) { return z > 0.f ? 1.f : p; }
+};
+template <> struct Act<SIRGCN_ACT_GELU> {
+    static __device__ __forceinline__ float f(float z, float) { return act_fwd(z, SIRGCN_ACT_GELU, 0.f); }
+    static __device__ __forceinline__ float d(float z, float) { return act_bwd(z, SIRGCN_ACT_GELU, 0.f); }
 };
 
-template <typename T, int VPL>
-__device__ __forceinline__ void load_row(const void *base, int64_t ld, int64_t row, const WalkCtx &c,
-                                         float (&dst)[VPL][VecTraits<T>::N], bool streaming) {
-    constexpr int NE = VecTraits<T>::N;
-    const T *p = reinterpret_cast<const T *>(base) + row * ld;
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-        const int vi = v * c.G + c.li;
-        if (vi < c.nvec) {
-            uint4 raw = streaming ? ldg_stream(p + vi * NE) : ldg_keep(p + vi * NE);
-            unpack<T>(raw, dst[v]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < NE; ++i) dst[v][i] = 0.f;
-        }
-    }
-}
+// ---- static configuration of one kernel variant ---------------------------------------------------
+// GS = a per-edge scale gathered by neighbour id is present ('sym' in the CSR walks; the CSC walk when dA
+// was not pre-scaled by the dQ pass)
+template <typename T, int VPL, int MODE, bool HAS_E, bool GS> struct Cfg {
+    static constexpr int NE = VecTraits<T>::N;
+    static constexpr int NGT = 1 + (MODE == kBwdK ? 1 : 0) + (HAS_E ? 1 : 0);   // gathered tables per edge
+    static constexpr int NST = 1 + (MODE == kBwdQ ? 1 : 0);                     // row-resident tables
+    static constexpr int U = (4 / (NGT * VPL)) > 0 ? (4 / (NGT * VPL)) : 1;     // edges per lane group per batch
+    static constexpr int S = (VPL == 4 || NST == 2) ? 3 : 4;                    // ring stages
+    static constexpr bool DE = HAS_E && MODE == kBwdQ;                          // edge ids kept for the dE store
+    static constexpr int kSlot = VPL * 512;                                     // bytes of one row image (32 lanes x 16 B)
+    static constexpr int kOffT2 = U * kSlot;                                    // second gathered table (dA, CSC walk)
+    static constexpr int kOffTE = (NGT - 1) * U * kSlot;                        // gathered edge term
+    static constexpr int kOffSelf = NGT * U * kSlot;
+    static constexpr int kOffSc = kOffSelf + NST * kSlot;                       // [U][32] float
+    static constexpr int kOffEid = kOffSc + (GS ? U * 128 : 0);                 // [U][32] int
+    static constexpr int kStage = kOffEid + (DE ? U * 128 : 0);
+};
 
-// Accumulates the contributions of positions [beg, end) of one row into acc (per-lane partial:
-// lane group gi holds the sum over the edges it visited; caller reduces across groups).
-template <typename T, int VPL, int MODE, bool HAS_E>
-__device__ __forceinline__ void walk_segment(const sirgcn_edge_args &a, int row, int beg, int end,
-                                             const WalkCtx &c, float (&acc)[VPL][VecTraits<T>::N]) {
-    constexpr int NE = VecTraits<T>::N;
-    constexpr int U = Unroll<VPL>::U;
-    constexpr unsigned kFull = 0xffffffffu;
+// per-warp shared memory: [S stages][batch descriptors int2 x cap][row boundaries][row scales]
+__host__ __device__ inline int desc_cap(int thr, int B) { return (SIRGCN_TILE_WORK + thr) / B + kTileRowCap + 8; }
+__host__ __device__ inline int tail_bytes(int cap) { return (cap * 8 + (kTileRowCap + 4) * 4 + kTileRowCap * 4 + 15) & ~15; }
 
-    // row-resident operands
-    float self[VPL][NE];
-    float ds[VPL][NE];  // backward-dQ: dA[row] * dst_scale[row]
-    if (MODE == kBwdK) {
-        load_row<T, VPL>(a.k, a.ldk, row, c, self, true);
-    } else {
-        load_row<T, VPL>(a.q, a.ldq, row, c, self, true);
-    }
-    if (MODE == kBwdQ) {
-        load_row<T, VPL>(a.da, a.lda, row, c, ds, true);
-        const float rs = a.dst_scale ? a.dst_scale[row] : 1.f;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v)
-#pragma unroll
-            for (int i = 0; i < NE; ++i) ds[v][i] *= rs;
-    }
-
-    const T *tab1 = reinterpret_cast<const T *>(MODE == kBwdK ? a.q : a.k);
-    const int64_t ld1 = MODE == kBwdK ? a.ldq : a.ldk;
-    const T *tab2 = reinterpret_cast<const T *>(a.da);  // kBwdK only
-    const T *etab = HAS_E ? reinterpret_cast<const T *>(a.e) : nullptr;
-    T *detab = (HAS_E && MODE == kBwdQ) ? reinterpret_cast<T *>(a.de) : nullptr;
-    const float *gscale = MODE == kBwdK ? a.dst_scale : a.src_scale;
-    const bool use_eid = HAS_E;
-
-    for (int base = beg; base < end; base += 32) {
-        const int n = min(32, end - base);
-        int my_idx = 0, my_eid = 0;
-        float my_gs = 1.f;
-        if (c.lane < n) {
-            my_idx = a.idx[base + c.lane];
-            if (use_eid) my_eid = a.eid[base + c.lane];
-            if (gscale) my_gs = gscale[my_idx];
-        }
-        for (int j = 0; j < n; j += c.NG * U) {
-            uint4 raw1[U][VPL], raw2[MODE == kBwdK ? U : 1][VPL], rawe[HAS_E ? U : 1][VPL];
-            int eids[U];
-            float sc[U];
-            bool ok[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int ej = j + u * c.NG + c.gi;
-                const int sl = ej & 31;
-                const int node = __shfl_sync(kFull, my_idx, sl);
-                sc[u] = __shfl_sync(kFull, my_gs, sl);
-                eids[u] = __shfl_sync(kFull, my_eid, sl);
-                ok[u] = ej < n;
-                if (ok[u]) {
-                    const T *p1 = tab1 + (int64_t)node * ld1;
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) {
-                        const int vi = v * c.G + c.li;
-                        if (vi < c.nvec) {
-                            raw1[u][v] = ldg_stream(p1 + vi * NE);
-                            if (MODE == kBwdK) raw2[MODE == kBwdK ? u : 0][v] = ldg_stream(tab2 + (int64_t)node * a.lda + vi * NE);
-                            if (HAS_E && etab) rawe[HAS_E ? u : 0][v] = ldg_stream(etab + (int64_t)eids[u] * a.lde + vi * NE);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!ok[u]) continue;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    const int vi = v * c.G + c.li;
-                    if (vi >= c.nvec) continue;
-                    float g1[NE], z[NE];
-                    unpack<T>(raw1[u][v], g1);
-#pragma unroll
-                    for (int i = 0; i < NE; ++i) z[i] = self[v][i] + g1[i];
-                    if (HAS_E && etab) {
-                        float ev[NE];
-                        unpack<T>(rawe[HAS_E ? u : 0][v], ev);
-#pragma unroll
-                        for (int i = 0; i < NE; ++i) z[i] += ev[i];
-                    }
-                    if (MODE == kFwd) {
-#pragma unroll
-                        for (int i = 0; i < NE; ++i) acc[v][i] += sc[u] * act_fwd(z[i], a.act, a.act_param);
-                    } else {
-                        float up[NE], val[NE];
-                        if (MODE == kBwdK) {
-                            unpack<T>(raw2[MODE == kBwdK ? u : 0][v], up);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < NE; ++i) up[i] = ds[v][i];
-                        }
-#pragma unroll
-                        for (int i = 0; i < NE; ++i) {
-                            val[i] = sc[u] * up[i] * act_bwd(z[i], a.act, a.act_param);
-                            acc[v][i] += val[i];
-                        }
-                        if (HAS_E && MODE == kBwdQ && detab) stg_vec(detab + (int64_t)eids[u] * a.ldde + vi * NE, pack<T>(val));
-                    }
-                }
-            }
-        }
-    }
-}
-
-template <int VPL, int NE>
-__device__ __forceinline__ void reduce_groups(float (&acc)[VPL][NE], int G) {
-    if (VPL == 1) {
-        for (int off = 16; off >= G; off >>= 1) {
-#pragma unroll
-            for (int i = 0; i < NE; ++i) acc[0][i] += __shfl_xor_sync(0xffffffffu, acc[0][i], off);
-        }
-    }
-}
-
-__device__ __forceinline__ WalkCtx make_ctx(const sirgcn_edge_args &a, int esize, int vpl) {
-    WalkCtx c;
-    c.lane = threadIdx.x & 31;
-    c.nvec = (a.d * esize + 15) / 16;
+__host__ __device__ inline int lanes_per_row(int nvec, int vpl) {
     int G = 32;
     if (vpl == 1) {
         G = 1;
-        while (G < c.nvec) G <<= 1;
+        while (G < nvec) G <<= 1;
     }
-    c.G = G;
-    c.NG = 32 / G;
-    c.gi = c.lane / G;
-    c.li = c.lane % G;
-    return c;
+    return G;
 }
 
-// ---- one warp per (short) row ---------------------------------------------------------------
-template <int VPL> struct MinBlocks { static constexpr int N = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1); };
+// =====================================================================================================
+// one warp per tile of short rows / per chunk of a long row
+//   pre-pass : the rows of the tile are cut into BATCHES of <= B = NG*U edges of ONE row; the list of
+//              batch descriptors {first position, row | count | first | last} is built lane-parallel
+//              (warp scan) in shared memory, so the hot loop has no cursor / row-boundary logic.
+//   hot loop : S-stage cp.async ring over the batch list; neighbour ids of the next batch are fetched
+//              straight into registers one iteration ahead (the lanes of a group read the same word).
+// =====================================================================================================
+template <typename T, int VPL, int MODE, bool HAS_E, int ACT, bool GS>
+__global__ void __launch_bounds__(kWarps * 32, 2) edge_walk_kernel(const sirgcn_edge_args a, const int chunk_mode) {
+    using C = Cfg<T, VPL, MODE, HAS_E, GS>;
+    constexpr int NE = C::NE, U = C::U, S = C::S;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvec = (a.d * (int)sizeof(T) + 15) / 16;
+    const int G = lanes_per_row(nvec, VPL), NG = 32 / G, gi = lane / G, li = lane % G;
 
-template <typename T, int VPL, int MODE, bool HAS_E>
-__global__ void __launch_bounds__(256, MinBlocks<VPL>::N) edge_rows_kernel(const sirgcn_edge_args a) {
-    constexpr int NE = VecTraits<T>::N;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= a.n_rows) return;
-    const int beg = a.indptr[row], end = a.indptr[row + 1];
-    if (end - beg > a.long_threshold) return;  // handled by the chunk kernels
-    const WalkCtx c = make_ctx(a, sizeof(T), VPL);
+    const float *gscale = MODE == kBwdK ? a.dst_scale : a.src_scale;             // indexed by idx  (GS)
+    const float *rscale = MODE == kBwdK ? a.src_scale : a.dst_scale;             // indexed by row
+    const bool has_rs = rscale != nullptr;
+    const int Ueff = min(U, 32 / NG);
+    const int B = NG * Ueff, logB = 31 - __clz(B);
+    const int thr = a.long_threshold;
+    const int cap = desc_cap(thr, B);
 
-    float acc[VPL][NE];
-#pragma unroll
-    for (int v = 0; v < VPL; ++v)
-#pragma unroll
-        for (int i = 0; i < NE; ++i) acc[v][i] = 0.f;
+    unsigned char *wsm = smem_raw + (size_t)warp * (S * C::kStage + tail_bytes(cap));
+    int2 *s_desc = reinterpret_cast<int2 *>(wsm + S * C::kStage);
+    int *s_ptr = reinterpret_cast<int *>(s_desc + cap);
+    float *s_rs = reinterpret_cast<float *>(s_ptr + kTileRowCap + 4);
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(wsm) + lane * 16;   // this lane's 16-B column of the ring
+    const uint32_t ring4 = (uint32_t)__cvta_generic_to_shared(wsm) + lane * 4;   // this lane's 4-B column
 
-    walk_segment<T, VPL, MODE, HAS_E>(a, row, beg, end, c, acc);
-    reduce_groups<VPL, NE>(acc, c.G);
+    // ---- which rows -------------------------------------------------------------------------------------
+    const int unit = blockIdx.x * kWarps + warp;
+    int r_beg, nrows;
+    const bool write_scaled = MODE == kBwdQ && a.da_scaled != nullptr && !chunk_mode;   // long rows: finalize kernel
+    if (chunk_mode) {
+        if (unit >= a.n_chunks) return;
+        r_beg = a.sched.long_rows[a.sched.chunk_lrow[unit]];
+        nrows = 1;
+        const int beg = a.sched.chunk_beg[unit];
+        if (lane == 0) {
+            s_ptr[0] = beg;
+            s_ptr[1] = min(beg + thr, a.indptr[r_beg + 1]);
+        }
+    } else {
+        if (unit >= a.n_tiles) return;
+        r_beg = a.tile_row[unit];
+        nrows = a.tile_row[unit + 1] - r_beg;
+        if (nrows <= 0) return;
+        for (int i = lane; i <= nrows; i += 32) s_ptr[i] = a.indptr[r_beg + i];
+    }
+    __syncwarp();
 
-    float rs = 1.f;
-    if (MODE == kFwd && a.dst_scale) rs = a.dst_scale[row];
-    if (MODE == kBwdK && a.src_scale) rs = a.src_scale[row];
-    if (c.gi == 0) {
-        T *o = reinterpret_cast<T *>(a.out) + (int64_t)row * a.ldo;
+    // ---- pre-pass: batch list ---------------------------------------------------------------------------
+    int total = 0;
+    for (int j0 = 0; j0 < nrows; j0 += 32) {
+        const int i = j0 + lane;
+        int beg = 0, deg = 0, nb = 0;
+        if (i < nrows) {
+            beg = s_ptr[i];
+            deg = s_ptr[i + 1] - beg;
+            if (chunk_mode || deg <= thr) nb = max(1, (deg + B - 1) >> logB);    // empty row: one batch of 0 edges (A[u] = 0)
+            if (has_rs) s_rs[i] = rscale[r_beg + i];
+        }
+        int incl = nb;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const int vi = v * c.G + c.li;
-            if (vi < c.nvec) {
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int off = total + incl - nb;
+        for (int k = 0; k < nb; ++k)
+            s_desc[off + k] = make_int2(beg + (k << logB),
+                                        i | (min(B, deg - (k << logB)) << 8) | (k == 0 ? 1 << 16 : 0) | (k == nb - 1 ? 1 << 17 : 0));
+        total += __shfl_sync(kFull, incl, 31);
+    }
+    __syncwarp();
+
+    // ---- lane constants --------------------------------------------------------------------------------------
+    bool vok[VPL];
 #pragma unroll
-                for (int i = 0; i < NE; ++i) acc[v][i] *= rs;
-                stg_vec(o + vi * NE, pack<T>(acc[v]));
+    for (int v = 0; v < VPL; ++v) vok[v] = v * G + li < nvec;
+    int slot[U];          // position of this lane group's u-th edge inside a batch (64 => never valid)
+#pragma unroll
+    for (int u = 0; u < U; ++u) slot[u] = (u < Ueff && vok[0]) ? gi * Ueff + u : 64;   // a group's edges are consecutive
+    const int esz = (int)sizeof(T);
+    const char *tab1 = reinterpret_cast<const char *>(MODE == kBwdK ? a.q : a.k) + li * 16;   // gathered by idx
+    const uint32_t ld1 = (uint32_t)((MODE == kBwdK ? a.ldq : a.ldk) * esz);
+    const char *tab2 = reinterpret_cast<const char *>(a.da) + li * 16;                        // CSC walk: gathered by idx
+    const uint32_t ld2 = (uint32_t)(a.lda * esz);
+    const char *selft = reinterpret_cast<const char *>(MODE == kBwdK ? a.k : a.q) + li * 16;  // row resident
+    const uint32_t ldself = (uint32_t)((MODE == kBwdK ? a.ldk : a.ldq) * esz);
+    const char *etab = HAS_E ? reinterpret_cast<const char *>(a.e) + li * 16 : nullptr;
+    const uint32_t lde = (uint32_t)(a.lde * esz);
+    char *detab = C::DE ? reinterpret_cast<char *>(a.de) + li * 16 : nullptr;
+    const int32_t *idxp = a.idx + gi * Ueff;
+    const int32_t *eidp = HAS_E ? a.eid + gi * Ueff : nullptr;
+    const int vstride = G * 16;                                  // bytes between a lane's consecutive vectors of one row
+    // keep the 64-bit bases in registers (otherwise they are re-derived from the constant bank per access)
+    asm("" : "+l"(tab1)); asm("" : "+l"(tab2)); asm("" : "+l"(selft)); asm("" : "+l"(idxp));
+    if (HAS_E) { asm("" : "+l"(etab)); asm("" : "+l"(eidp)); }
+
+    // ---- neighbour ids of the next batch to issue, one iteration ahead ---------------------------------------
+    int nd[U], ne[HAS_E ? U : 1];
+    auto prefetch = [&](int b) {
+        if (b >= total) return;
+        const int2 d = s_desc[b];
+        const int cnt = (d.y >> 8) & 255;
+        const int32_t *ip = idxp + d.x;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (slot[u] < cnt) {
+                nd[u] = ldg_idx(ip + u);
+                if (HAS_E) ne[HAS_E ? u : 0] = ldg_idx(eidp + d.x + u);
             }
         }
-    }
-}
+    };
 
-// ---- one warp per chunk of a long row: fp32 partial ------------------------------------------
-template <typename T, int VPL, int MODE, bool HAS_E>
-__global__ void __launch_bounds__(256, MinBlocks<VPL>::N) edge_chunks_kernel(const sirgcn_edge_args a) {
-    constexpr int NE = VecTraits<T>::N;
-    const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (chunk >= a.n_chunks) return;
-    const int lrow = a.sched.chunk_lrow[chunk];
-    const int row = a.sched.long_rows[lrow];
-    const int beg = a.sched.chunk_beg[chunk];
-    const int end = min(beg + a.long_threshold, a.indptr[row + 1]);
-    const WalkCtx c = make_ctx(a, sizeof(T), VPL);
-
-    float acc[VPL][NE];
+    int istage = 0, cstage = 0;                                  // ring slots of the next issue / consume
+    auto issue = [&](int b) {
+        const int2 d = s_desc[b];
+        const int cnt = (d.y >> 8) & 255;
+        const uint32_t st = ring + istage * C::kStage;
+        const uint32_t st4 = ring4 + istage * C::kStage;
+        istage = istage + 1 == S ? 0 : istage + 1;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v)
+        for (int u = 0; u < U; ++u) {
+            if (slot[u] < cnt) {
+                const int node = nd[u];
+                const char *p1 = tab1 + (uint64_t)(uint32_t)node * ld1;
+                const char *p2 = MODE == kBwdK ? tab2 + (uint64_t)(uint32_t)node * ld2 : nullptr;
+                const char *pe = (HAS_E && etab) ? etab + (uint64_t)(uint32_t)ne[HAS_E ? u : 0] * lde : nullptr;
 #pragma unroll
-        for (int i = 0; i < NE; ++i) acc[v][i] = 0.f;
-
-    walk_segment<T, VPL, MODE, HAS_E>(a, row, beg, end, c, acc);
-    reduce_groups<VPL, NE>(acc, c.G);
-
-    if (c.gi == 0) {
-        float *o = a.partial + (int64_t)chunk * (c.nvec * NE);
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const int vi = v * c.G + c.li;
-            if (vi < c.nvec) {
-#pragma unroll
-                for (int i = 0; i < NE; i += 4)
-                    *reinterpret_cast<float4 *>(o + vi * NE + i) =
-                        make_float4(acc[v][i], acc[v][i + 1], acc[v][i + 2], acc[v][i + 3]);
+                for (int v = 0; v < VPL; ++v) {
+                    if (v > 0 && !vok[v]) continue;
+                    switch (u) {   // immediate ring offsets
+#define SIRGCN_CP(UU)                                                                                      \
+    case UU:                                                                                               \
+        cp_async16<(UU * VPL) * 512>(st + v * 512, p1 + v * vstride);                                      \
+        if (MODE == kBwdK) cp_async16<C::kOffT2 + (UU * VPL) * 512>(st + v * 512, p2 + v * vstride);       \
+        if (HAS_E && etab) cp_async16<C::kOffTE + (UU * VPL) * 512>(st + v * 512, pe + v * vstride);       \
+        break;
+                        SIRGCN_CP(0) SIRGCN_CP(1) SIRGCN_CP(2) SIRGCN_CP(3)
+#undef SIRGCN_CP
+                    }
+                }
+                if (GS) {
+                    const float *gp = gscale + node;
+                    switch (u) {
+                        case 0: cp_async4<C::kOffSc>(st4, gp); break;
+                        case 1: cp_async4<C::kOffSc + 128>(st4, gp); break;
+                        case 2: cp_async4<C::kOffSc + 256>(st4, gp); break;
+                        default: cp_async4<C::kOffSc + 384>(st4, gp); break;
+                    }
+                }
+                if (C::DE) {
+                    switch (u) {
+                        case 0: sts32<C::kOffEid>(st4, ne[0]); break;
+                        case 1: sts32<C::kOffEid + 128>(st4, ne[HAS_E && U > 1 ? 1 : 0]); break;
+                        case 2: sts32<C::kOffEid + 256>(st4, ne[HAS_E && U > 2 ? 2 : 0]); break;
+                        default: sts32<C::kOffEid + 384>(st4, ne[HAS_E && U > 3 ? 3 : 0]); break;
+                    }
+                }
             }
+        }
+        if (d.y & (1 << 16)) {                                   // first batch of a row: its own operands
+            const uint32_t row = (uint32_t)(r_beg + (d.y & 255));
+            const char *ps = selft + (uint64_t)row * ldself;
+            const char *pa = MODE == kBwdQ ? tab2 + (uint64_t)row * ld2 : nullptr;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                if (!vok[v]) continue;
+                cp_async16<C::kOffSelf>(st + v * 512, ps + v * vstride);
+                if (MODE == kBwdQ) cp_async16<C::kOffSelf + C::kSlot>(st + v * 512, pa + v * vstride);
+            }
+        }
+        prefetch(b + 1);
+    };
+
+    // ---- arithmetic of one landed batch -------------------------------------------------------------------
+    float self[VPL][NE], ds[MODE == kBwdQ ? VPL : 1][NE], acc[VPL][NE];
+    float rs = 1.f;
+    const float ap = a.act_param;
+    const float zero[NE] = {};
+    auto consume = [&](int b) {
+        const int2 d = s_desc[b];
+        const int cnt = (d.y >> 8) & 255;
+        const uint32_t st = ring + cstage * C::kStage;
+        const uint32_t st4 = ring4 + cstage * C::kStage;
+        cstage = cstage + 1 == S ? 0 : cstage + 1;
+        if (d.y & (1 << 16)) {
+            if (has_rs) rs = s_rs[d.y & 255];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                if (vok[v]) {
+                    add_vec<T>(lds128<C::kOffSelf>(st + v * 512), zero, self[v]);
+                    if (MODE == kBwdQ) {
+                        add_vec<T>(lds128<C::kOffSelf + C::kSlot>(st + v * 512), zero, ds[MODE == kBwdQ ? v : 0]);
+#pragma unroll
+                        for (int i = 0; i < NE; ++i) ds[MODE == kBwdQ ? v : 0][i] *= rs;
+                        if (write_scaled && gi == 0) {
+                            char *o = reinterpret_cast<char *>(a.da_scaled) + (uint64_t)(uint32_t)(r_beg + (d.y & 255)) * (uint32_t)(a.ldds * esz) + li * 16;
+                            stg_vec(o + v * vstride, pack<T>(ds[MODE == kBwdQ ? v : 0]));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NE; ++i) acc[v][i] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (slot[u] >= cnt) continue;
+            float sc = 1.f;
+            if (GS) sc = __uint_as_float(u == 0 ? lds32<C::kOffSc>(st4) : u == 1 ? lds32<C::kOffSc + 128>(st4)
+                                         : u == 2 ? lds32<C::kOffSc + 256>(st4) : lds32<C::kOffSc + 384>(st4));
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                if (v > 0 && !vok[v]) continue;
+                uint4 r1, r2 = make_uint4(0, 0, 0, 0), re = make_uint4(0, 0, 0, 0);
+                switch (u) {
+#define SIRGCN_LD(UU)                                                                               \
+    case UU:                                                                                        \
+        r1 = lds128<(UU * VPL) * 512>(st + v * 512);                                                \
+        if (MODE == kBwdK) r2 = lds128<C::kOffT2 + (UU * VPL) * 512>(st + v * 512);                 \
+        if (HAS_E) re = lds128<C::kOffTE + (UU * VPL) * 512>(st + v * 512);                         \
+        break;
+                    SIRGCN_LD(0) SIRGCN_LD(1) SIRGCN_LD(2) default: SIRGCN_LD(3)
+#undef SIRGCN_LD
+                }
+                float z[NE];
+                add_vec<T>(r1, self[v], z);
+                if (HAS_E && a.e) add_vec<T>(re, z, z);
+                if (MODE == kFwd) {
+#pragma unroll
+                    for (int i = 0; i < NE; ++i) {
+                        if (GS) acc[v][i] += sc * Act<ACT>::f(z[i], ap);
+                        else acc[v][i] += Act<ACT>::f(z[i], ap);
+                    }
+                } else if (ACT == SIRGCN_ACT_RELU && !C::DE) {
+                    // σ' ∈ {0,1}: predicated accumulate of the upstream gradient, no multiply
+                    float t[NE];
+                    if (MODE == kBwdK) {
+                        if (GS) {
+                            add_vec<T>(r2, zero, t);
+#pragma unroll
+                            for (int i = 0; i < NE; ++i) t[i] = fmaf(sc, t[i], acc[v][i]);
+                        } else {
+                            add_vec<T>(r2, acc[v], t);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NE; ++i) t[i] = GS ? fmaf(sc, ds[MODE == kBwdQ ? v : 0][i], acc[v][i]) : acc[v][i] + ds[MODE == kBwdQ ? v : 0][i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NE; ++i) acc[v][i] = z[i] > 0.f ? t[i] : acc[v][i];
+                } else {
+                    float up[NE], val[NE];
+                    if (MODE == kBwdK) {
+                        add_vec<T>(r2, zero, up);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NE; ++i) up[i] = ds[MODE == kBwdQ ? v : 0][i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NE; ++i) {
+                        val[i] = (GS ? sc * up[i] : up[i]) * Act<ACT>::d(z[i], ap);
+                        acc[v][i] += val[i];
+                    }
+                    if (C::DE) {
+                        if (detab) {
+                            const int eidv = (int)(u == 0 ? lds32<C::kOffEid>(st4) : u == 1 ? lds32<C::kOffEid + 128>(st4)
+                                                   : u == 2 ? lds32<C::kOffEid + 256>(st4) : lds32<C::kOffEid + 384>(st4));
+                            stg_vec(detab + (uint64_t)(uint32_t)eidv * (uint32_t)(a.ldde * esz) + v * vstride, pack<T>(val));
+                        }
+                    }
+                }
+            }
+        }
+        if (d.y & (1 << 17)) {                                   // last batch of a row: reduce + store
+            if (VPL == 1) {
+                for (int off = 16; off >= G; off >>= 1) {
+#pragma unroll
+                    for (int i = 0; i < NE; ++i) acc[0][i] += __shfl_xor_sync(kFull, acc[0][i], off);
+                }
+            }
+            if (gi == 0) {
+                if (chunk_mode) {
+                    float *o = a.partial + (int64_t)unit * (nvec * NE) + li * NE;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        if (!vok[v]) continue;
+#pragma unroll
+                        for (int i = 0; i < NE; i += 4)
+                            *reinterpret_cast<float4 *>(o + v * G * NE + i) =
+                                make_float4(acc[v][i], acc[v][i + 1], acc[v][i + 2], acc[v][i + 3]);
+                    }
+                } else {
+                    const float os = MODE == kBwdQ ? 1.f : rs;   // bwd-dQ folded dst_scale into ds
+                    char *o = reinterpret_cast<char *>(a.out) + (uint64_t)(uint32_t)(r_beg + (d.y & 255)) * (uint32_t)(a.ldo * esz) + li * 16;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        if (!vok[v]) continue;
+#pragma unroll
+                        for (int i = 0; i < NE; ++i) acc[v][i] *= os;
+                        stg_vec(o + v * vstride, pack<T>(acc[v]));
+                    }
+                }
+            }
+        }
+    };
+
+    // ---- S-stage software pipeline; one commit per iteration keeps wait_group<S-1> exact ---------------------
+    prefetch(0);
+#pragma unroll 1
+    for (int it = 0; it < total + S - 1; ++it) {
+        if (it < total) issue(it);
+        cp_async_commit();
+        if (it >= S - 1) {
+            cp_async_wait<S - 1>();
+            consume(it - (S - 1));
         }
     }
 }
@@ -290,27 +491,63 @@ __global__ void __launch_bounds__(256) edge_long_finalize_kernel(const sirgcn_ed
             r[i] = s * rs;
         }
         stg_vec(o + vi * NE, pack<T>(r));
+        if (MODE == kBwdQ && a.da_scaled) {      // dA[row] * dst_scale[row] for the CSC walk (may alias dA: all chunks are done)
+            const float ds = a.dst_scale ? a.dst_scale[row] : 1.f;
+            float g[NE];
+            unpack<T>(ldg_keep(reinterpret_cast<const T *>(a.da) + (int64_t)row * a.lda + vi * NE), g);
+#pragma unroll
+            for (int i = 0; i < NE; ++i) g[i] *= ds;
+            stg_vec(reinterpret_cast<T *>(a.da_scaled) + (int64_t)row * a.ldds + vi * NE, pack<T>(g));
+        }
     }
+}
+
+template <typename T, int VPL, int MODE, bool HAS_E, int ACT, bool GS>
+int launch_gs(const sirgcn_edge_args &a, cudaStream_t st) {
+    using C = Cfg<T, VPL, MODE, HAS_E, GS>;
+    constexpr int NE = VecTraits<T>::N;
+    const int nvec = (a.d * (int)sizeof(T) + 15) / 16;
+    const int NG = 32 / lanes_per_row(nvec, VPL);
+    const int B = NG * std::min(C::U, 32 / NG);
+    const size_t smem = (size_t)kWarps * (C::S * C::kStage + tail_bytes(desc_cap(a.long_threshold, B)));
+    if (smem > 227 * 1024) {
+        set_error("long_threshold %d needs %zu bytes of shared memory per CTA (max 232448)", a.long_threshold, smem);
+        return SIRGCN_EUNSUP;
+    }
+    auto kern = edge_walk_kernel<T, VPL, MODE, HAS_E, ACT, GS>;
+    SIRGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (a.n_tiles > 0) {
+        kern<<<(unsigned)((a.n_tiles + kWarps - 1) / kWarps), kWarps * 32, smem, st>>>(a, 0);
+        SIRGCN_LAUNCHED();
+    }
+    if (a.n_chunks > 0) {
+        kern<<<(unsigned)((a.n_chunks + kWarps - 1) / kWarps), kWarps * 32, smem, st>>>(a, 1);
+        SIRGCN_LAUNCHED();
+        const size_t fsmem = (size_t)8 * nvec * NE * sizeof(float);
+        edge_long_finalize_kernel<T, MODE><<<(unsigned)a.n_long, 256, fsmem, st>>>(a);
+        SIRGCN_LAUNCHED();
+    }
+    return SIRGCN_OK;
+}
+
+template <typename T, int VPL, int MODE, bool HAS_E, int ACT>
+int launch_act(const sirgcn_edge_args &a, cudaStream_t st) {
+    const float *gscale = MODE == kBwdK ? a.dst_scale : a.src_scale;
+    return gscale ? launch_gs<T, VPL, MODE, HAS_E, ACT, true>(a, st) : launch_gs<T, VPL, MODE, HAS_E, ACT, false>(a, st);
 }
 
 template <typename T, int VPL, int MODE, bool HAS_E>
 int launch_mode(const sirgcn_edge_args &a, cudaStream_t st) {
-    constexpr int NE = VecTraits<T>::N;
-    if (a.n_rows > 0) {
-        const unsigned grid = (unsigned)((a.n_rows + 7) / 8);
-        edge_rows_kernel<T, VPL, MODE, HAS_E><<<grid, 256, 0, st>>>(a);
-        SIRGCN_LAUNCHED();
+    switch (a.act) {
+        case SIRGCN_ACT_RELU: return launch_act<T, VPL, MODE, HAS_E, SIRGCN_ACT_RELU>(a, st);
+        case SIRGCN_ACT_GELU: return launch_act<T, VPL, MODE, HAS_E, SIRGCN_ACT_GELU>(a, st);
+        case SIRGCN_ACT_IDENTITY: {                      // identity == leaky ReLU with slope 1 (exactly)
+            sirgcn_edge_args b = a;
+            b.act_param = 1.f;
+            return launch_act<T, VPL, MODE, HAS_E, SIRGCN_ACT_LEAKY_RELU>(b, st);
+        }
+        default: return launch_act<T, VPL, MODE, HAS_E, SIRGCN_ACT_LEAKY_RELU>(a, st);
     }
-    if (a.n_chunks > 0) {
-        const unsigned grid = (unsigned)((a.n_chunks + 7) / 8);
-        edge_chunks_kernel<T, VPL, MODE, HAS_E><<<grid, 256, 0, st>>>(a);
-        SIRGCN_LAUNCHED();
-        const int nvec = (a.d * (int)sizeof(T) + 15) / 16;
-        const size_t smem = (size_t)8 * nvec * NE * sizeof(float);
-        edge_long_finalize_kernel<T, MODE><<<(unsigned)a.n_long, 256, smem, st>>>(a);
-        SIRGCN_LAUNCHED();
-    }
-    return SIRGCN_OK;
 }
 
 template <typename T, int MODE>
@@ -328,15 +565,9 @@ int launch_vpl(const sirgcn_edge_args &a, cudaStream_t st) {
 
 }  // namespace
 
-// one translation unit per element type (parallel compilation): edge_f32.cu / edge_bf16.cu / edge_f16.cu
-template <typename T>
-int edge_launch(const sirgcn_edge_args &a, int mode, cudaStream_t st) {
-    switch (mode) {
-        case kFwd: return launch_vpl<T, kFwd>(a, st);
-        case kBwdQ: return launch_vpl<T, kBwdQ>(a, st);
-        default: return launch_vpl<T, kBwdK>(a, st);
-    }
+// one translation unit per (element type, mode): edge_<type>_<mode>.cu  (parallel compilation)
+template <typename T, int MODE> int edge_launch(const sirgcn_edge_args &a, cudaStream_t st) {
+    return launch_vpl<T, MODE>(a, st);
 }
 
 }  // namespace sirgcn
-

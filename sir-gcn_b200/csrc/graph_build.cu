@@ -93,6 +93,18 @@ __global__ void schedule_kernel(const int32_t *__restrict__ indptr, int32_t num_
     }
 }
 
+// tile_row[t] = min { r : indptr[r] + ROW_COST*r >= t*TILE_WORK }  (see sirgcn.h "Work tiles")
+__global__ void tiles_kernel(const int32_t *__restrict__ indptr, int32_t num_rows, int64_t n_tiles,
+                             int32_t *__restrict__ tile_row) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= num_rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w = (int64_t)indptr[r] + (int64_t)SIRGCN_ROW_COST * r;
+        const int64_t t_hi = w / SIRGCN_TILE_WORK;
+        const int64_t t_lo = r == 0 ? 0 : ((int64_t)indptr[r - 1] + (int64_t)SIRGCN_ROW_COST * (r - 1)) / SIRGCN_TILE_WORK + 1;
+        for (int64_t t = t_lo; t <= t_hi && t < n_tiles; ++t) tile_row[t] = (int32_t)r;
+        if (r == num_rows) tile_row[n_tiles] = num_rows;
+    }
+}
+
 struct SortScratch {
     int32_t *keys[2];
     int32_t *vals[2];
@@ -161,6 +173,25 @@ size_t sirgcn_csr_build_workspace_bytes(int64_t num_edges, int32_t num_nodes) {
     if (num_edges <= 0) return 256;
     const size_t arr = align_up((size_t)num_edges * sizeof(int32_t));
     return 4 * arr + align_up(cub_temp_bytes(num_edges, key_bits(num_nodes))) + 256;
+}
+
+int64_t sirgcn_num_tiles(int32_t num_rows, int64_t num_edges) {
+    if (num_rows <= 0) return 0;
+    return (num_edges + (int64_t)SIRGCN_ROW_COST * num_rows) / SIRGCN_TILE_WORK + 1;
+}
+
+int sirgcn_tiles_build(const int32_t *indptr, int32_t num_rows, int64_t num_edges, int32_t *tile_row, void *stream) {
+    using namespace sirgcn;
+    SIRGCN_CHECK_ARG(num_rows >= 0 && num_edges >= 0, "bad num_rows/num_edges");
+    if (num_rows == 0) return SIRGCN_OK;
+    SIRGCN_CHECK_ARG(indptr && tile_row, "indptr/tile_row is NULL");
+    const int64_t n_tiles = sirgcn_num_tiles(num_rows, num_edges);
+    SIRGCN_CHECK_ARG(n_tiles < (1LL << 31), "too many tiles");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    tiles_kernel<<<std::min(blocks_for((int64_t)num_rows + 1), (unsigned)kNumSMs * 16), kThreads, 0, st>>>(
+        indptr, num_rows, n_tiles, tile_row);
+    SIRGCN_LAUNCHED();
+    return SIRGCN_OK;
 }
 
 int sirgcn_schedule_build(const int32_t *indptr, int32_t num_rows, int32_t long_threshold,

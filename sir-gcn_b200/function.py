@@ -60,7 +60,7 @@ EDGE_TIMERS = None
 
 
 def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da, e, out, de,
-               dst_scale, src_scale):
+               dst_scale, src_scale, da_scaled=None):
     if not (rows.indptr.is_cuda and q.is_cuda and k.is_cuda and out.is_cuda):
         raise RuntimeError("SIR-GCN edge kernels need CUDA tensors (no CPU fallback)")
     a = _lib.EdgeArgs()
@@ -79,11 +79,15 @@ def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da
     a.out, a.ldo = out.data_ptr(), _ld(out)
     if de is not None:
         a.de, a.ldde = de.data_ptr(), _ld(de)
+    if da_scaled is not None:
+        a.da_scaled, a.ldds = da_scaled.data_ptr(), _ld(da_scaled)
     a.dst_scale = None if dst_scale is None else dst_scale.data_ptr()
     a.src_scale = None if src_scale is None else src_scale.data_ptr()
     a.sched, a.n_long, a.n_chunks = rows.sched, rows.n_long, rows.n_chunks
     partial = rows.partial(d, dtype)
     a.partial = None if partial is None else partial.data_ptr()
+    a.tile_row = None if rows.tile_row is None else rows.tile_row.data_ptr()
+    a.n_tiles = rows.n_tiles
     dev = rows.indptr.device
     with torch.cuda.device(dev):
         if EDGE_TIMERS is not None:
@@ -107,13 +111,17 @@ def edge_forward(csr: CompressedRows, q, k, e, dst_scale, src_scale, act, act_pa
     return out
 
 
-def edge_backward_q(csr, q, k, e, da, dst_scale, src_scale, act, act_param, want_de, out=None):
+def edge_backward_q(csr, q, k, e, da, dst_scale, src_scale, act, act_param, want_de, out=None,
+                    scale_da_inplace=False):
+    """dQ over the CSR (+ dE).  With `scale_da_inplace` (and a destination scale), the pass also overwrites
+    dA[u] by dst_scale[u]·dA[u], so the CSC pass that follows can gather an already scaled table and needs
+    no per-edge scale lookup (pass it dst_scale=None)."""
     d = q.shape[1]
     dq = _alloc_table(csr.n_rows, d, q.dtype, q.device) if out is None else out
     de = _alloc_table(e.shape[0], d, q.dtype, q.device) if (want_de and e is not None) else None
     if csr.n_rows:
         _edge_call("sirgcn_edge_bwd_q", csr, d, q.dtype, act, act_param, q, k, da, e, dq, de,
-                   dst_scale, src_scale)
+                   dst_scale, src_scale, da if (scale_da_inplace and dst_scale is not None) else None)
     return dq, de
 
 
@@ -218,8 +226,10 @@ class SIRLayerFunction(torch.autograd.Function):
         ds, ss = g.scales(ctx.agg_type)
         dqk = (torch.empty if ldp == d else torch.zeros)(qk.shape, dtype=qk.dtype, device=qk.device)
         dq, dk = dqk[:, :d], dqk[:, ldp:ldp + d]
-        _, de = edge_backward_q(g.csr, q, k, e, da, ds, ss, ctx.act, ctx.act_param, need[3], out=dq)
-        edge_backward_k(g.csc, q, k, e, da, ds, ss, ctx.act, ctx.act_param, out=dk)
+        # the dQ pass leaves dA scaled by the destination coefficient (in place: `da` is ours)
+        _, de = edge_backward_q(g.csr, q, k, e, da, ds, ss, ctx.act, ctx.act_param, need[3], out=dq,
+                                scale_da_inplace=True)
+        edge_backward_k(g.csc, q, k, e, da, None, ss, ctx.act, ctx.act_param, out=dk)
         del da
         dw_qk = gemm.linear_wgrad(dqk, feat, w_qk.dtype) if need[1] else None
         db_qk = dqk.sum(0).to(w_qk.dtype) if (need[2] and ctx.has_bias[0]) else None

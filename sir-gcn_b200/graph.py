@@ -37,6 +37,7 @@ class CompressedRows:
         self.n_long, self.n_chunks = int(counts[0]), int(counts[1])
         self.sched = _lib.Schedule(*[_lib.ptr(t).value for t in sched])
         self._partial = {}
+        self.tile_row, self.n_tiles = _build_tiles(indptr, self.n_rows, self.num_pos)
 
     def partial(self, d, dtype):
         """fp32 scratch for the long-row partial sums (cached per (d, dtype))."""
@@ -57,6 +58,19 @@ class CompressedRows:
         indptr = (self.indptr[lo:hi + 1] - beg).contiguous()
         eid = None if self.eid is None else self.eid[beg:end].contiguous()
         return CompressedRows(indptr, self.idx[beg:end].contiguous(), eid, self.long_threshold)
+
+
+def _build_tiles(indptr, n_rows, num_pos):
+    """work tiles of the edge kernels (sirgcn.h "Work tiles"): (tile_row int32 [n_tiles+1], n_tiles)"""
+    if not indptr.is_cuda or n_rows == 0:
+        return None, 0
+    L = _lib.lib()
+    n_tiles = int(L.sirgcn_num_tiles(C.c_int32(n_rows), C.c_int64(num_pos)))
+    tile_row = torch.empty(n_tiles + 1, dtype=torch.int32, device=indptr.device)
+    with torch.cuda.device(indptr.device):
+        _lib.check(L.sirgcn_tiles_build(_lib.ptr(indptr), C.c_int32(n_rows), C.c_int64(num_pos),
+                                        _lib.ptr(tile_row), _lib.stream_ptr(indptr.device)), "sirgcn_tiles_build")
+    return tile_row, n_tiles
 
 
 def _sched_alloc(num_pos, thr, device):

@@ -5,6 +5,8 @@ bf16/fp16 within 2e-2 relative, where "relative" is max|a-b| / max|b| over the t
 """
 import os
 
+os.environ.setdefault("CUBLAS_WORKSPACE_CONFIG", ":4096:8")   # as the reference's set_seed() does (e.g. zinc/train.py:19-29)
+
 import pytest
 import torch
 from torch import nn
@@ -66,6 +68,33 @@ def test_csr_build_bit_exact(n, e, seed):
             assert cb[first:first + nch].tolist() == [int(rows.indptr[r]) + 64 * c for c in range(nch)]
 
 
+@pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (7, 40, 3), (3, 2000, 5), (50000, 50, 6), (20000, 300000, 7)])
+def test_work_tiles(n, e, seed):
+    """tile_row[t] = min{r : indptr[r] + 4 r >= 512 t}: every row in exactly one tile, <= 128 rows per tile"""
+    src, dst = rand_graph(n, e, seed, hub=0 if e > 100 else None)
+    g = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
+    for rows in (g.csr, g.csc):
+        w = rows.indptr.cpu().long() + 4 * torch.arange(n + 1)
+        assert rows.n_tiles == int(w[-1]) // 512 + 1
+        want = torch.searchsorted(w, 512 * torch.arange(rows.n_tiles), right=False)
+        got = rows.tile_row.cpu().long()
+        assert torch.equal(got[:-1], want) and int(got[-1]) == n
+        assert int((got[1:] - got[:-1]).max()) <= 128 and int(got[0]) == 0
+
+
+def test_mostly_isolated_nodes():
+    """50,000 nodes, 50 edges: empty rows are zero-filled by the tile walk (b_R after W_R, conv.py:65)"""
+    n, e, d = 50000, 50, 64
+    src, dst = rand_graph(n, e, 6)
+    g = Graph(src.to(DEV), dst.to(DEV), n)
+    torch.manual_seed(0)
+    q, k = torch.randn(n, d, device=DEV), torch.randn(n, d, device=DEV)
+    out = EdgeAggregate.apply(q, k, None, g, "sum", _lib.ACT_RELU, 0.0)
+    ref = oracle_edge(src, dst, n, q.cpu(), k.cpu(), None, "sum", nn.ReLU())
+    assert rel_err(out, ref) < FP32_RTOL
+    assert int((out.abs().sum(1) > 0).sum()) <= e
+
+
 def test_graph_without_edge_ids_and_cpu_rejection():
     src, dst = rand_graph(50, 400, 1)
     g = Graph(src.to(DEV), dst.to(DEV), 50, need_eid=False)
@@ -78,7 +107,7 @@ def test_graph_without_edge_ids_and_cpu_rejection():
 
 
 # ---- fused edge stage on raw tables --------------------------------------------------------------
-def oracle_edge(src, dst, n, q, k, e, agg, act):
+def oracle_edge(src, dst, n, q, k, e, agg, act):  # noqa: E302
     g = RefGraph(src, dst, n)
     in_norm, out_norm = _norms(g, agg, q)
     z = q.index_select(0, g.dst) + k.index_select(0, g.src)
