@@ -95,9 +95,11 @@ int sirgcn_schedule_build(const int32_t *indptr, int32_t num_rows, int32_t long_
  * w(r) = indptr[r] + SIRGCN_ROW_COST * r, tile t holds the rows with floor(w(r)/SIRGCN_TILE_WORK) == t:
  *   tile_row[t] = min { r : w(r) >= t * SIRGCN_TILE_WORK },   tile_row[n_tiles] = num_rows,
  *   n_tiles = sirgcn_num_tiles(num_rows, num_edges) = (num_edges + ROW_COST*num_rows) / TILE_WORK + 1.
- * A tile never holds more than TILE_WORK / ROW_COST = 128 rows.  Purely a function of indptr, so
+ * A tile never holds more than TILE_WORK / ROW_COST = 64 rows.  Purely a function of indptr, so
  * the decomposition — and with it every floating-point summation order — is reproducible. */
-#define SIRGCN_TILE_WORK 512
+#ifndef SIRGCN_TILE_WORK
+#define SIRGCN_TILE_WORK 256
+#endif
 #define SIRGCN_ROW_COST 4
 int64_t sirgcn_num_tiles(int32_t num_rows, int64_t num_edges);
 int sirgcn_tiles_build(const int32_t *indptr, int32_t num_rows, int64_t num_edges,

@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsirgcn.so")
+LIB_PATH = os.environ.get("SIRGCN_LIB") or os.path.join(_HERE, "libsirgcn.so")   # override: kernel-variant A/B runs
 
 F32, BF16, F16 = 0, 1, 2
 ACT_IDENTITY, ACT_RELU, ACT_LEAKY_RELU, ACT_GELU = 0, 1, 2, 3

@@ -25,8 +25,20 @@ namespace sirgcn {
 namespace {
 
 enum Mode { kFwd = 0, kBwdQ = 1, kBwdK = 2 };
-constexpr int kWarps = 8;            // warps per CTA
-constexpr int kTileRowCap = 128;     // max rows per tile = tile_work / row_cost (graph_build.cu)
+#ifndef SIRGCN_WARPS
+#define SIRGCN_WARPS 4
+#endif
+#ifndef SIRGCN_STAGES
+#define SIRGCN_STAGES 2
+#endif
+#ifndef SIRGCN_STAGES_Q
+#define SIRGCN_STAGES_Q 2
+#endif
+#ifndef SIRGCN_MIN_CTAS
+#define SIRGCN_MIN_CTAS 6
+#endif
+constexpr int kWarps = SIRGCN_WARPS;  // warps per CTA
+constexpr int kTileRowCap = SIRGCN_TILE_WORK / SIRGCN_ROW_COST;     // max rows per tile (graph_build.cu)
 constexpr unsigned kFull = 0xffffffffu;
 
 // cp.async with a 32-bit shared address + immediate offset (no generic->shared conversion per copy)
@@ -107,7 +119,8 @@ template <typename T, int VPL, int MODE, bool HAS_E, bool GS> struct Cfg {
     static constexpr int NGT = 1 + (MODE == kBwdK ? 1 : 0) + (HAS_E ? 1 : 0);   // gathered tables per edge
     static constexpr int NST = 1 + (MODE == kBwdQ ? 1 : 0);                     // row-resident tables
     static constexpr int U = (4 / (NGT * VPL)) > 0 ? (4 / (NGT * VPL)) : 1;     // edges per lane group per batch
-    static constexpr int S = (VPL == 4 || NST == 2) ? 3 : 4;                    // ring stages
+    static constexpr int S = VPL == 4 ? (SIRGCN_STAGES_Q < 3 ? SIRGCN_STAGES_Q : 3)
+                                      : (NST == 2 ? SIRGCN_STAGES_Q : SIRGCN_STAGES);   // ring stages
     static constexpr bool DE = HAS_E && MODE == kBwdQ;                          // edge ids kept for the dE store
     static constexpr int kSlot = VPL * 512;                                     // bytes of one row image (32 lanes x 16 B)
     static constexpr int kOffT2 = U * kSlot;                                    // second gathered table (dA, CSC walk)
@@ -140,7 +153,7 @@ __host__ __device__ inline int lanes_per_row(int nvec, int vpl) {
 //              straight into registers one iteration ahead (the lanes of a group read the same word).
 // =====================================================================================================
 template <typename T, int VPL, int MODE, bool HAS_E, int ACT, bool GS>
-__global__ void __launch_bounds__(kWarps * 32, 2) edge_walk_kernel(const sirgcn_edge_args a, const int chunk_mode) {
+__global__ void __launch_bounds__(kWarps * 32, SIRGCN_MIN_CTAS) edge_walk_kernel(const sirgcn_edge_args a, const int chunk_mode) {
     using C = Cfg<T, VPL, MODE, HAS_E, GS>;
     constexpr int NE = C::NE, U = C::U, S = C::S;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 
-DEFAULT_LONG_THRESHOLD = 512
+DEFAULT_LONG_THRESHOLD = 256
 
 
 class CompressedRows:

@@ -70,16 +70,16 @@ def test_csr_build_bit_exact(n, e, seed):
 
 @pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (7, 40, 3), (3, 2000, 5), (50000, 50, 6), (20000, 300000, 7)])
 def test_work_tiles(n, e, seed):
-    """tile_row[t] = min{r : indptr[r] + 4 r >= 512 t}: every row in exactly one tile, <= 128 rows per tile"""
+    """tile_row[t] = min{r : indptr[r] + 4 r >= 256 t}: every row in exactly one tile, <= 64 rows per tile"""
     src, dst = rand_graph(n, e, seed, hub=0 if e > 100 else None)
     g = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
     for rows in (g.csr, g.csc):
         w = rows.indptr.cpu().long() + 4 * torch.arange(n + 1)
-        assert rows.n_tiles == int(w[-1]) // 512 + 1
-        want = torch.searchsorted(w, 512 * torch.arange(rows.n_tiles), right=False)
+        assert rows.n_tiles == int(w[-1]) // 256 + 1
+        want = torch.searchsorted(w, 256 * torch.arange(rows.n_tiles), right=False)
         got = rows.tile_row.cpu().long()
         assert torch.equal(got[:-1], want) and int(got[-1]) == n
-        assert int((got[1:] - got[:-1]).max()) <= 128 and int(got[0]) == 0
+        assert int((got[1:] - got[:-1]).max()) <= 64 and int(got[0]) == 0
 
 
 def test_mostly_isolated_nodes():
