@@ -234,7 +234,8 @@ def run_gpu(args, w):
     # ---- graph + features -------------------------------------------------------------------
     t_build = time.perf_counter()
     if world == 1:
-        src, dst, n = synth.powerlaw(n, e, alpha=2.3, max_deg=w["max_deg"], seed=0, device=dev)
+        # counter-based generator: the SAME global graph whatever the world size (partition.py slices it)
+        src, dst, n = synth.powerlaw_hashed(n, e, alpha=2.3, max_deg=w["max_deg"], seed=0, device=dev)
         graph = Graph(src, dst, n, need_eid=False, keep_coo=False)
         del src, dst
         n_local, e_local = n, e
@@ -327,6 +328,13 @@ def run_gpu(args, w):
         stages[name] = {"ms": avg, "bytes": by, "gbs": by / avg / 1e6, "frac": by / avg / 1e6 / peak,
                         "share_of_step": ms / (ms_step * args.steps)}
     dom = max(stages, key=lambda k: stages[k]["ms"]) if stages else None
+    traffic = None      # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if dom and world == 1 and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj["workload"] == {"nodes": n, "edges": e, "d": d, "dtype": w["dtype"]}:
+            traffic = tj.get(dom)
     tot_ms = sum(s["ms"] for s in stages.values())
     tot_by = sum(s["bytes"] for s in stages.values())
 
@@ -371,7 +379,7 @@ def run_gpu(args, w):
             "clocks": clocks,
             "roofline": None if dom is None else {
                 "bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": stages[dom]["gbs"] / 8000.0,
                 "edge_stage_total": {"ms": tot_ms, "bytes": tot_by, "gbs": tot_by / tot_ms / 1e6,
                                      "frac": tot_by / tot_ms / 1e6 / peak,

@@ -84,6 +84,14 @@ int sirgcn_csr_build(const int32_t *src, const int32_t *dst, int64_t num_edges, 
                      int32_t *counts /* [4] device */,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* One compressed-row structure from (key, other) pairs: rows = key values in [0, num_rows), stable
+ * (ties keep input order); `other` values are carried along untouched (they may be GLOBAL node ids of
+ * a row-partitioned graph, partition.py).  eid_sorted (input position of every stored entry) may be NULL. */
+size_t sirgcn_rows_build_workspace_bytes(int64_t num_pos, int32_t num_rows);
+int sirgcn_rows_build(const int32_t *key, const int32_t *other, int64_t num_pos, int32_t num_rows,
+                      int32_t *indptr, int32_t *other_sorted, int32_t *eid_sorted,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
 /* Schedule only (graph already in CSR form, e.g. generated on device): fills one
  * sirgcn_schedule and counts[0..1] = {n_long, n_chunks}. */
 int sirgcn_schedule_build(const int32_t *indptr, int32_t num_rows, int32_t long_threshold,
@@ -162,6 +170,17 @@ int sirgcn_edge_fwd(const sirgcn_edge_args *args, void *stream);
 int sirgcn_edge_bwd_q(const sirgcn_edge_args *args, void *stream);
 /* dK[v] = sum_{p in row v} c_p * dA[idx[p]] (*) act'(q[idx[p]] + k[v] + e[eid[p]])                (CSC walk) */
 int sirgcn_edge_bwd_k(const sirgcn_edge_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense projections on the tcgen05 tensor cores (bf16 / fp16 tables, fp32 accumulation in TMEM, TMA-fed).
+ * Replaces the cuBLAS GEMMs behind nn.Linear: linear_query ‖ linear_key as ONE concatenated projection
+ * (conv.py:60-61), linear_relation (conv.py:65) and their input gradients.
+ *   C[m, n] = A[m, k] · B[n, k]^T (+ bias[n], fp32, may be NULL)        all row-major, ld* in elements
+ * forward: B = the weight as nn.Linear stores it ([out, in]);  dgrad: B = W^T (contiguous [in, out]).
+ * n, k and every ld must be multiples of 8 (16-byte rows); fp32 tables are not handled here (tcgen05 has
+ * no IEEE-fp32 MMA; the fp32 parity target is 1e-5). */
+int sirgcn_gemm_tn(const void *a, int64_t lda, const void *b, int64_t ldb, void *c, int64_t ldc,
+                   const float *bias, int64_t m, int32_t n, int32_t k, int32_t dtype, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Split path for arbitrary (non-elementwise) σ, agg_type 'max'/'min', and the

@@ -211,6 +211,36 @@ int sirgcn_schedule_build(const int32_t *indptr, int32_t num_rows, int32_t long_
     return SIRGCN_OK;
 }
 
+size_t sirgcn_rows_build_workspace_bytes(int64_t num_pos, int32_t num_rows) {
+    return sirgcn_csr_build_workspace_bytes(num_pos, num_rows);
+}
+
+int sirgcn_rows_build(const int32_t *key, const int32_t *other, int64_t num_pos, int32_t num_rows,
+                      int32_t *indptr, int32_t *other_sorted, int32_t *eid_sorted,
+                      void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace sirgcn;
+    SIRGCN_CHECK_ARG(num_pos >= 0 && num_pos < (1LL << 31), "num_pos=%lld out of int32 range", (long long)num_pos);
+    SIRGCN_CHECK_ARG(num_rows >= 0 && indptr, "bad num_rows / indptr");
+    SIRGCN_CHECK_ARG(num_pos == 0 || (key && other && other_sorted), "key/other arrays are NULL");
+    const size_t need = sirgcn_rows_build_workspace_bytes(num_pos, num_rows);
+    if (workspace_bytes < need || (!workspace && num_pos > 0)) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+        return SIRGCN_ENOSPC;
+    }
+    SortScratch ws{};
+    if (num_pos > 0) {
+        const size_t arr = align_up((size_t)num_pos * sizeof(int32_t));
+        char *base = reinterpret_cast<char *>(workspace);
+        ws.keys[0] = reinterpret_cast<int32_t *>(base);
+        ws.keys[1] = reinterpret_cast<int32_t *>(base + arr);
+        ws.vals[0] = reinterpret_cast<int32_t *>(base + 2 * arr);
+        ws.vals[1] = reinterpret_cast<int32_t *>(base + 3 * arr);
+        ws.cub_tmp = base + 4 * arr;
+        ws.cub_bytes = workspace_bytes - 4 * arr;
+    }
+    return build_one(key, other, num_pos, num_rows, indptr, other_sorted, eid_sorted, ws, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int sirgcn_csr_build(const int32_t *src, const int32_t *dst, int64_t num_edges, int32_t num_nodes,
                      int32_t *indptr_in, int32_t *col_src, int32_t *eid_in,
                      int32_t *indptr_out, int32_t *row_dst, int32_t *eid_out,

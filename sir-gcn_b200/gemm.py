@@ -11,8 +11,52 @@ IEEE-fp32 MMA and the fp32 parity target is 1e-5 relative.
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
+
 import torch
 import torch.nn.functional as F
+
+from . import _lib
+
+# SIRGCN_GEMM=cublas routes the 16-bit projections through the library instead (A/B measurements)
+_USE_TC = os.environ.get("SIRGCN_GEMM", "tcgen05") != "cublas"
+
+
+def _rows16(t):
+    """2-D, unit column stride, 16-byte aligned rows of a 16-bit table"""
+    return (t.dim() == 2 and t.stride(1) == 1 and t.data_ptr() % 16 == 0 and
+            (t.shape[0] <= 1 or t.stride(0) % 8 == 0))
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def tc_eligible(x, n, k):
+    """the hand-written tcgen05 kernel handles CUDA bf16/fp16 operands with 16-byte rows (n, k multiples of 8)"""
+    return (_USE_TC and x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and n % 8 == 0 and k % 8 == 0
+            and x.shape[0] < 2 ** 31)
+
+
+def gemm_tn(a, b, bias=None, out=None):
+    """C[m, n] = a[m, k] · b[n, k]^T (+ bias) on the tcgen05 tensor cores (sirgcn_gemm_tn, include/sirgcn.h)"""
+    m, k = a.shape
+    n = b.shape[0]
+    if not _rows16(a):
+        a = a.contiguous()
+    if not _rows16(b):
+        b = b.contiguous()
+    if out is None:
+        out = torch.empty((m, n), dtype=a.dtype, device=a.device)
+    if bias is not None:
+        bias = bias.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().sirgcn_gemm_tn(_lib.ptr(a), C.c_int64(_ld(a)), _lib.ptr(b), C.c_int64(_ld(b)), _lib.ptr(out),
+                                       C.c_int64(_ld(out)), _lib.ptr(bias), C.c_int64(m), C.c_int32(n), C.c_int32(k),
+                                       C.c_int32(_lib.DTYPE_CODE[a.dtype]), _lib.stream_ptr(a.device))
+    _lib.check(rc, "sirgcn_gemm_tn")
+    return out
 
 
 def linear(x, weight, bias=None):
@@ -28,13 +72,21 @@ def linear_forward(x, weight, bias):
         bias = None if bias is None else bias.to(dt)
     elif weight.dtype != x.dtype:
         weight = weight.to(x.dtype)
-        bias = None if bias is None else bias.to(x.dtype)
-    return F.linear(x, weight, bias)
+    if x.dim() == 2 and tc_eligible(x, weight.shape[0], weight.shape[1]):
+        return gemm_tn(x, weight.detach(), bias)
+    return F.linear(x, weight, None if bias is None else bias.to(x.dtype))
 
 
 def linear_dgrad(dy, weight, pad_to=None):
     """dX = dY · W; with pad_to, the result is a [M, pad_to] buffer whose extra columns are zero"""
     k = weight.shape[1]
+    if dy.dim() == 2 and tc_eligible(dy, k, weight.shape[0]):
+        wt = weight.detach().t().contiguous()               # [in, out]: K-major B operand of the TN kernel (tiny)
+        if pad_to is None or pad_to == k:
+            return gemm_tn(dy, wt)
+        out = torch.zeros((dy.shape[0], pad_to), dtype=dy.dtype, device=dy.device)
+        gemm_tn(dy, wt, out=out[:, :k])
+        return out
     if pad_to is None or pad_to == k:
         return dy @ weight
     out = torch.zeros((dy.shape[0], pad_to), dtype=dy.dtype, device=dy.device)

@@ -4,24 +4,29 @@ correctness oracle is "G-rank result == 1-rank result" (SURVEY.md §8e).
 
 Rank r owns node rows [r*n_pad, min(N, (r+1)*n_pad)), n_pad = ceil(N/G): its slice of H, Q, K, A, the
 in-CSR rows of those destinations (column ids stay GLOBAL source ids) and the out-CSC rows of those
-sources (row ids stay GLOBAL destination ids).  Per layer and direction there is exactly one exchange:
+sources (row ids stay GLOBAL destination ids).  Per layer there are three exchanges, two of them hidden:
 
-    forward   K_full  = all_gather(K_loc)                 -> edge_fwd   over the local CSR rows
-    backward  dQ_loc  = edge_bwd_q over the local CSR rows (re-uses K_full)
-              Q_full, dA_full = all_gather(Q_loc), all_gather(dA_loc)
-              dK_loc  = edge_bwd_k over the local CSC rows
+    forward   K_full  = all_gather(K_loc)                 -> edge_fwd over the local CSR rows   (exposed)
+              Q_full  = all_gather(Q_loc)  issued right behind it on NCCL's stream; it is only needed by the
+                        backward CSC pass, so it travels while the forward edge kernel runs
+    backward  dA_loc *= dst coefficient;  dA_full = all_gather(dA_loc)  travels while
+              dQ_loc  = edge_bwd_q over the local CSR rows (re-uses K_full) runs
+              dK_loc  = edge_bwd_k over the local CSC rows (Q_full, dA_full, K_loc)
     weights   replicated; dW summed with all_reduce
 
-Because gathered tables are laid out [G*n_pad, d], a global node id indexes them directly.
+Gathered tables are laid out [G*n_pad, ld], so a global node id indexes them directly.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
+import torch.nn.functional as F
 
+from . import _lib
 from . import function as F_
-from . import gemm
-from .graph import CompressedRows, Graph
+from .graph import DEFAULT_LONG_THRESHOLD, CompressedRows, Graph
 
 
 class CudaEdgeBackend:
@@ -31,8 +36,32 @@ class CudaEdgeBackend:
     backward_k = staticmethod(F_.edge_backward_k)
 
 
+def build_rows(key, other, n_rows, long_threshold=DEFAULT_LONG_THRESHOLD):
+    """CompressedRows over rows = `key` values in [0, n_rows) carrying `other` (any int32 payload, e.g. global
+    node ids), by the stable GPU sort of sirgcn_rows_build."""
+    if not key.is_cuda:
+        raise RuntimeError("build_rows needs CUDA index tensors (no CPU fallback)")
+    dev = key.device
+    key, other = key.to(torch.int32).contiguous(), other.to(torch.int32).contiguous()
+    e = int(key.numel())
+    indptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    out = torch.empty(e, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    nbytes = L.sirgcn_rows_build_workspace_bytes(C.c_int64(e), C.c_int32(n_rows))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.sirgcn_rows_build(_lib.ptr(key), _lib.ptr(other), C.c_int64(e), C.c_int32(n_rows), _lib.ptr(indptr),
+                                 _lib.ptr(out), None, _lib.ptr(ws), C.c_size_t(nbytes), _lib.stream_ptr(dev))
+    _lib.check(rc, "sirgcn_rows_build")
+    del ws
+    return CompressedRows(indptr, out, None, long_threshold)
+
+
 class RowPartition:
-    """Local slice of a graph for rank `rank` of `world` (see module docstring)."""
+    """Local slice of a graph for rank `rank` of `world` (see module docstring).
+
+    csr: rows = local destinations, idx = GLOBAL sources;  csc: rows = local sources, idx = GLOBAL destinations.
+    in_norm / out_norm / inv_in_deg: fp32 [G*n_pad] GLOBAL coefficient vectors (padding = 1)."""
 
     def __init__(self, num_nodes, rank, world, csr_local, csc_local, in_norm, out_norm, inv_in_deg, group=None):
         self.num_nodes_, self.rank, self.world, self.group = int(num_nodes), rank, world, group
@@ -40,54 +69,116 @@ class RowPartition:
         self.lo = min(self.num_nodes_, rank * self.n_pad)
         self.hi = min(self.num_nodes_, self.lo + self.n_pad)
         self.csr, self.csc = csr_local, csc_local
-        # per-node coefficients, padded to G*n_pad so that gathered-table indices are valid
         self.in_norm, self.out_norm, self.inv_in_deg = in_norm, out_norm, inv_in_deg
         self.num_local_edges = csr_local.num_pos
+
+    @staticmethod
+    def bounds(num_nodes, rank, world):
+        n_pad = (num_nodes + world - 1) // world
+        lo = min(num_nodes, rank * n_pad)
+        return n_pad, lo, min(num_nodes, lo + n_pad)
 
     @property
     def n_local(self):
         return self.hi - self.lo
 
+    # ---- construction ---------------------------------------------------------------------------------
+    @classmethod
+    def from_csr_csc(cls, csr: CompressedRows, csc: CompressedRows, num_nodes, rank, world, group=None,
+                     in_norm=None, out_norm=None, inv_in_deg=None):
+        """slice replicated whole-graph structures (tests, small graphs)"""
+        n = int(num_nodes)
+        n_pad, lo, hi = cls.bounds(n, rank, world)
+        if in_norm is None:
+            in_deg = (csr.indptr[1:] - csr.indptr[:-1]).clamp(min=1).to(torch.float32)
+            out_deg = (csc.indptr[1:] - csc.indptr[:-1]).clamp(min=1).to(torch.float32)
+            in_norm, out_norm, inv_in_deg = 1.0 / torch.sqrt(in_deg), 1.0 / torch.sqrt(out_deg), 1.0 / in_deg
+        pad = lambda t: torch.cat([t, t.new_ones(world * n_pad - n)]) if world * n_pad > n else t
+        return cls(n, rank, world, csr.slice_rows(lo, hi), csc.slice_rows(lo, hi),
+                   pad(in_norm), pad(out_norm), pad(inv_in_deg), group)
+
     @classmethod
     def from_graph(cls, graph: Graph, rank, world, group=None):
         """slice an already converted (replicated) Graph; the caller may drop `graph` afterwards"""
-        n = graph.num_nodes()
-        n_pad = (n + world - 1) // world
-        lo = min(n, rank * n_pad)
-        hi = min(n, lo + n_pad)
-        pad = lambda t: torch.cat([t, t.new_ones(world * n_pad - n)]) if world * n_pad > n else t
-        return cls(n, rank, world, graph.csr.slice_rows(lo, hi), graph.csc.slice_rows(lo, hi),
-                   pad(graph.in_norm), pad(graph.out_norm), pad(graph.inv_in_deg), group)
+        return cls.from_csr_csc(graph.csr, graph.csc, graph.num_nodes(), rank, world, group,
+                                graph.in_norm, graph.out_norm, graph.inv_in_deg)
+
+    @classmethod
+    def from_local_edges(cls, num_nodes, rank, world, in_src, in_dst, out_src, out_dst, group=None,
+                         long_threshold=DEFAULT_LONG_THRESHOLD, in_indptr=None):
+        """build from this rank's two edge lists (GLOBAL ids): the edges whose destination is local
+        (in_src -> in_dst) and the edges whose source is local (out_src -> out_dst).  When the first list is
+        already destination-sorted, pass its local row pointer `in_indptr` instead of `in_dst`.  Degree
+        coefficients of the whole graph are assembled with one all_gather each."""
+        n = int(num_nodes)
+        n_pad, lo, hi = cls.bounds(n, rank, world)
+        dev = in_src.device
+        nl = hi - lo
+        if in_indptr is not None:
+            csr = CompressedRows(in_indptr.to(torch.int32).contiguous(), in_src.to(torch.int32).contiguous(), None,
+                                 long_threshold)
+        else:
+            csr = build_rows(in_dst - lo, in_src, nl, long_threshold)
+        csc = build_rows(out_src - lo, out_dst, nl, long_threshold)
+        in_deg = (csr.indptr[1:] - csr.indptr[:-1]).clamp(min=1).to(torch.float32)
+        out_deg = (csc.indptr[1:] - csc.indptr[:-1]).clamp(min=1).to(torch.float32)
+
+        def gather(v):
+            buf = torch.ones(n_pad, dtype=torch.float32, device=dev)
+            buf[:nl] = v
+            full = torch.empty(world * n_pad, dtype=torch.float32, device=dev)
+            if world > 1:
+                dist.all_gather_into_tensor(full, buf, group=group)
+            else:
+                full.copy_(buf)
+            return full
+        return cls(n, rank, world, csr, csc, gather(1.0 / torch.sqrt(in_deg)), gather(1.0 / torch.sqrt(out_deg)),
+                   gather(1.0 / in_deg), group)
+
+    @classmethod
+    def synthetic_powerlaw(cls, num_nodes, num_edges, rank, world, alpha=2.3, max_deg=None, seed=0, device="cuda",
+                           group=None, long_threshold=DEFAULT_LONG_THRESHOLD):
+        """this rank's slice of synth.powerlaw_hashed (the SAME global graph on every world size), generated on
+        the device without any edge exchange"""
+        from . import synth
+        indptr = synth.powerlaw_indptr(num_nodes, num_edges, alpha, max_deg, seed, device)
+        n_pad, lo, hi = cls.bounds(num_nodes, rank, world)
+        in_src, _ = synth.powerlaw_hashed_rows(indptr, num_nodes, lo, hi, seed, want_dst=False)
+        out_src, out_dst = synth.powerlaw_hashed_cols(indptr, num_nodes, lo, hi, seed)
+        in_indptr = indptr[lo:hi + 1] - indptr[lo]
+        del indptr
+        return cls.from_local_edges(num_nodes, rank, world, in_src, None, out_src, out_dst, group, long_threshold,
+                                    in_indptr=in_indptr)
+
+    # ---- coefficients --------------------------------------------------------------------------------------
+    def _rows(self, v):
+        return v[self.lo:self.lo + max(self.n_local, 1)]
 
     def scales_rows(self, agg_type):
         """(dst_scale, src_scale) for the CSR walks: dst = local row, src = global id"""
         if agg_type == "sym":
-            return self.in_norm[self.lo:self.lo + max(self.n_local, 1)], self.out_norm
+            return self._rows(self.in_norm), self.out_norm
         if agg_type == "mean":
-            return self.inv_in_deg[self.lo:self.lo + max(self.n_local, 1)], None
+            return self._rows(self.inv_in_deg), None
         return None, None
 
-    def scales_cols(self, agg_type):
-        """(dst_scale, src_scale) for the CSC walk: dst = global id, src = local row"""
-        if agg_type == "sym":
-            return self.in_norm, self.out_norm[self.lo:self.lo + max(self.n_local, 1)]
-        if agg_type == "mean":
-            return self.inv_in_deg, None
-        return None, None
+    def scale_cols_rows(self, agg_type):
+        """row (= local source) scale of the CSC walk; its destination scale is folded into dA before the gather"""
+        return self._rows(self.out_norm) if agg_type == "sym" else None
 
-    def all_gather_rows(self, local):
-        """[n_local, d] -> [G*n_pad, d] (rows of rank r at r*n_pad ...), padded rows are zero"""
-        d = local.shape[1]
-        if local.shape[0] != self.n_pad or not local.is_contiguous():
-            buf = local.new_zeros((self.n_pad, d))
-            buf[: local.shape[0]].copy_(local)
-            local = buf
-        full = local.new_empty((self.world * self.n_pad, d))
+    # ---- collectives ------------------------------------------------------------------------------------------
+    def new_rows(self, ld, dtype, device):
+        """[n_pad, ld] buffer whose first n_local rows are this rank's slice of a table"""
+        return torch.empty((self.n_pad, ld), dtype=dtype, device=device)
+
+    def all_gather_rows(self, local_pad, async_op=False):
+        """[n_pad, ld] -> ([G*n_pad, ld], work handle or None); rows of rank r land at r*n_pad"""
+        full = local_pad.new_empty((self.world * self.n_pad, local_pad.shape[1]))
         if self.world == 1:
-            full.copy_(local)
-        else:
-            dist.all_gather_into_tensor(full, local, group=self.group)
-        return full
+            full.copy_(local_pad)
+            return full, None
+        work = dist.all_gather_into_tensor(full, local_pad, group=self.group, async_op=async_op)
+        return full, (work if async_op else None)
 
     def all_reduce_(self, t):
         if self.world > 1 and t is not None:
@@ -95,53 +186,88 @@ class RowPartition:
         return t
 
 
+def _wait(work):
+    if work is not None:
+        work.wait()        # stream-level wait: the current stream waits for NCCL's, the host does not block
+
+
 class PartitionedSIRLayerFunction(torch.autograd.Function):
-    """SIRLayerFunction for a row-partitioned graph: same arithmetic per row, one all-gather per
-    direction, weight gradients all-reduced (so every rank ends with the full-graph gradient)."""
+    """SIRLayerFunction for a row-partitioned graph: same arithmetic per row; K all-gathered in forward, Q and
+    the pre-scaled dA all-gathered behind the edge kernels, weight gradients all-reduced (every rank ends with
+    the full-graph gradient)."""
 
     @staticmethod
-    def forward(ctx, feat_loc, w_qk, b_qk, w_r, b_r, part: RowPartition, agg_type, act, act_param, d, backend):
-        qk = gemm.linear_forward(feat_loc, w_qk, b_qk)
-        ldp = qk.shape[1] // 2
-        q, k = qk[:, :d], qk[:, ldp:ldp + d]
-        q._sirgcn_padded = True
-        k_full = part.all_gather_rows(k)
+    def forward(ctx, feat, w_q, b_q, w_k, w_r, b_r, part: RowPartition, agg_type, act, act_param, backend):
+        n, d, dt, dev = part.n_local, w_q.shape[0], feat.dtype, feat.device
+        ld = F_._pad_cols(d, dt)
+        alloc = (torch.zeros if ld != d else torch.empty)
+        k_pad = alloc((part.n_pad, ld), dtype=dt, device=dev)
+        q_pad = alloc((part.n_pad, ld), dtype=dt, device=dev)
+        wq, wk = w_q.to(dt), w_k.to(dt)
+        torch.mm(feat, wk.t(), out=k_pad[:n, :d]) if ld == d else k_pad[:n, :d].copy_(feat @ wk.t())
+        k_full, wk_h = part.all_gather_rows(k_pad, async_op=True)
+        q_loc = F.linear(feat, wq, None if b_q is None else b_q.to(dt))
+        q_pad[:n, :d].copy_(q_loc)
+        del q_loc
+        q_full, wq_h = part.all_gather_rows(q_pad, async_op=True)       # consumed by backward only
+        q, k = q_pad[:n, :d], k_pad[:n, :d]
+        q._sirgcn_padded = k._sirgcn_padded = True
+        kf = k_full[:, :d]
+        kf._sirgcn_padded = True
         ds, ss = part.scales_rows(agg_type)
-        a = backend.forward(part.csr, q, k_full, None, ds, ss, act, act_param)
-        out = gemm.linear_forward(a, w_r, b_r)
-        ctx.save_for_backward(feat_loc, qk, k_full, a, w_qk, w_r)
-        ctx.part, ctx.agg_type, ctx.act, ctx.act_param, ctx.d, ctx.backend = part, agg_type, act, act_param, d, backend
-        ctx.has_bias = (b_qk is not None, b_r is not None)
+        _wait(wk_h)
+        a = backend.forward(part.csr, q, kf, None, ds, ss, act, act_param)
+        out = F.linear(a, w_r.to(dt), None if b_r is None else b_r.to(dt))
+        ctx.save_for_backward(feat, q_pad, k_pad, k_full, q_full, a, w_q, w_k, w_r)
+        ctx.q_work = wq_h
+        ctx.part, ctx.agg_type, ctx.act, ctx.act_param, ctx.backend = part, agg_type, act, act_param, backend
+        ctx.has_bias = (b_q is not None, b_r is not None)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        feat, qk, k_full, a, w_qk, w_r = ctx.saved_tensors
-        part, d, be = ctx.part, ctx.d, ctx.backend
-        ldp = qk.shape[1] // 2
-        q, k = qk[:, :d], qk[:, ldp:ldp + d]
-        q._sirgcn_padded = k._sirgcn_padded = True
+        feat, q_pad, k_pad, k_full, q_full, a, w_q, w_k, w_r = ctx.saved_tensors
+        part, be = ctx.part, ctx.backend
+        n, d, dt, dev = part.n_local, w_q.shape[0], q_pad.dtype, q_pad.device
+        ld = q_pad.shape[1]
         need = ctx.needs_input_grad
-        gout = gout.to(qk.dtype)
+        gout = gout.to(dt)
         gout = gout if gout.stride(-1) == 1 else gout.contiguous()
-        dw_r = part.all_reduce_(gemm.linear_wgrad(gout, a, w_r.dtype)) if need[3] else None
-        db_r = part.all_reduce_(gout.sum(0).to(w_r.dtype)) if (need[4] and ctx.has_bias[1]) else None
-        da = gemm.linear_dgrad(gout, w_r.to(qk.dtype), pad_to=F_._pad_cols(d, qk.dtype))[:, :d]
-        da._sirgcn_padded = True
-        dqk = (torch.empty if ldp == d else torch.zeros)(qk.shape, dtype=qk.dtype, device=qk.device)
-        dq, dk = dqk[:, :d], dqk[:, ldp:ldp + d]
+        dw_r = (gout.t() @ a).to(w_r.dtype) if need[4] else None
+        db_r = gout.sum(0).to(w_r.dtype) if (need[5] and ctx.has_bias[1]) else None
+        # dA, scaled by the destination coefficient BEFORE it travels: the CSC pass then needs no scale lookup
+        alloc = (torch.zeros if ld != d else torch.empty)
+        da_pad = alloc((part.n_pad, ld), dtype=dt, device=dev)
+        da = da_pad[:n, :d]
+        torch.mm(gout, w_r.to(dt), out=da) if ld == d else da.copy_(gout @ w_r.to(dt))
         ds, ss = part.scales_rows(ctx.agg_type)
-        be.backward_q(part.csr, q, k_full, None, da, ds, ss, ctx.act, ctx.act_param, False, out=dq)
-        del k_full
-        q_full, da_full = part.all_gather_rows(q), part.all_gather_rows(da)
-        del da
-        ds, ss = part.scales_cols(ctx.agg_type)
-        be.backward_k(part.csc, q_full, k, None, da_full, ds, ss, ctx.act, ctx.act_param, out=dk)
-        del q_full, da_full
-        dw_qk = part.all_reduce_(gemm.linear_wgrad(dqk, feat, w_qk.dtype)) if need[1] else None
-        db_qk = part.all_reduce_(dqk.sum(0).to(w_qk.dtype)) if (need[2] and ctx.has_bias[0]) else None
-        dfeat = gemm.linear_dgrad(dqk, w_qk.to(qk.dtype)).to(feat.dtype) if need[0] else None
-        return dfeat, dw_qk, db_qk, dw_r, db_r, None, None, None, None, None, None
+        if ds is not None:
+            da.mul_(ds[:n].to(dt).unsqueeze(1))
+        da._sirgcn_padded = True
+        da_full, wa_h = part.all_gather_rows(da_pad, async_op=True)      # travels while dQ is computed
+        q, k = q_pad[:n, :d], k_pad[:n, :d]
+        q._sirgcn_padded = k._sirgcn_padded = True
+        kf, qf, daf = k_full[:, :d], q_full[:, :d], da_full[:, :d]
+        kf._sirgcn_padded = qf._sirgcn_padded = daf._sirgcn_padded = True
+        dq = F_._alloc_table(n, d, dt, dev, zero=ld != d)
+        dk = F_._alloc_table(n, d, dt, dev, zero=ld != d)
+        be.backward_q(part.csr, q, kf, None, da, None, ss, ctx.act, ctx.act_param, False, out=dq)
+        _wait(ctx.q_work)
+        _wait(wa_h)
+        be.backward_k(part.csc, qf, k, None, daf, None, part.scale_cols_rows(ctx.agg_type), ctx.act, ctx.act_param,
+                      out=dk)
+        featd = feat.to(dt)
+        dw_q = part.all_reduce_((dq.t() @ featd).to(w_q.dtype)) if need[1] else None
+        db_q = part.all_reduce_(dq.sum(0).to(w_q.dtype)) if (need[2] and ctx.has_bias[0]) else None
+        dw_k = part.all_reduce_((dk.t() @ featd).to(w_k.dtype)) if need[3] else None
+        dw_r = part.all_reduce_(dw_r)
+        db_r = part.all_reduce_(db_r)
+        dfeat = None
+        if need[0]:
+            dfeat = dq @ w_q.to(dt)
+            dfeat.addmm_(dk, w_k.to(dt))
+            dfeat = dfeat.to(feat.dtype)
+        return dfeat, dw_q, db_q, dw_k, dw_r, db_r, None, None, None, None, None
 
 
 def partitioned_sirconv(layer, part: RowPartition, feat_loc, backend=CudaEdgeBackend):
@@ -156,7 +282,6 @@ def partitioned_sirconv(layer, part: RowPartition, feat_loc, backend=CudaEdgeBac
         raise NotImplementedError("dropout inside the partitioned layer is not supported")
     if feat_loc.shape[0] != part.n_local:
         raise ValueError(f"feat_loc has {feat_loc.shape[0]} rows, this rank owns {part.n_local}")
-    w, b, d, _ = layer._cat_qk_weights(feat_loc.dtype)
-    lr = layer.linear_relation
-    return PartitionedSIRLayerFunction.apply(feat_loc, w, b, lr.weight, lr.bias, part, layer._agg_type,
-                                             known[0], known[1], d, backend)
+    lq, lk, lr = layer.linear_query, layer.linear_key, layer.linear_relation
+    return PartitionedSIRLayerFunction.apply(feat_loc, lq.weight, lq.bias, lk.weight, lr.weight, lr.bias, part,
+                                             layer._agg_type, known[0], known[1], backend)

@@ -79,6 +79,73 @@ def powerlaw(num_nodes, num_edges, alpha=2.3, max_deg=None, seed=0, device="cpu"
     return src, dst, num_nodes
 
 
+# ---- counter-based variant: any rank can enumerate any slice of the SAME global graph --------------------
+def _hash_src(e, num_nodes, seed):
+    """source node of global edge number e (int64 tensor, e < 2^32): murmur-style 32-bit finalizer, then a
+    multiply-shift onto [0, num_nodes); a pure function of (e, seed), so every rank of a partitioned run sees
+    the same graph without exchanging edges"""
+    m = 0xFFFFFFFF
+    x = (e ^ (int(seed) * 0x9E3779B1 & m)) & m
+    x = ((x ^ (x >> 16)) * 0x45D9F3B) & m
+    x = ((x ^ (x >> 16)) * 0x45D9F3B) & m
+    x = x ^ (x >> 16)
+    return (x * int(num_nodes)) >> 32
+
+
+def powerlaw_indptr(num_nodes, num_edges, alpha=2.3, max_deg=None, seed=0, device="cpu"):
+    """global in-CSR row pointer (int64 [N+1]) of the power-law graph; identical on every rank"""
+    gen = _gen(seed, device)
+    if max_deg is None:
+        max_deg = max(64, num_nodes // 4)
+    deg = _powerlaw_degrees(num_nodes, num_edges, alpha, max_deg, gen, device)
+    indptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=device)
+    torch.cumsum(deg, 0, out=indptr[1:])
+    return indptr
+
+
+def powerlaw_hashed_rows(indptr, num_nodes, lo, hi, seed=0, index_dtype=torch.int32, step=1 << 27, want_dst=True):
+    """edges whose DESTINATION lies in [lo, hi) of the hashed power-law graph, destination-sorted:
+    (src global ids, dst global ids) — the in-CSR slice of a destination-row partition"""
+    dev = indptr.device
+    e_lo, e_hi = int(indptr[lo]), int(indptr[hi])
+    n = e_hi - e_lo
+    src = torch.empty(n, dtype=index_dtype, device=dev)
+    for a in range(e_lo, e_hi, step):
+        b = min(e_hi, a + step)
+        src[a - e_lo:b - e_lo] = _hash_src(torch.arange(a, b, dtype=torch.int64, device=dev), num_nodes, seed).to(index_dtype)
+    if not want_dst:
+        return src, None
+    deg = indptr[lo + 1:hi + 1] - indptr[lo:hi]
+    dst = torch.repeat_interleave(torch.arange(lo, hi, dtype=index_dtype, device=dev), deg, output_size=n)
+    return src, dst
+
+
+def powerlaw_hashed_cols(indptr, num_nodes, lo, hi, seed=0, index_dtype=torch.int32, step=1 << 27):
+    """edges whose SOURCE lies in [lo, hi), in global edge order (i.e. destination-sorted): (src, dst) global
+    ids — the out-CSC slice of a destination-row partition; found by scanning the hash of every edge number"""
+    dev = indptr.device
+    num_edges = int(indptr[-1])
+    srcs, dsts = [], []
+    for a in range(0, num_edges, step):
+        b = min(num_edges, a + step)
+        e = torch.arange(a, b, dtype=torch.int64, device=dev)
+        s = _hash_src(e, num_nodes, seed)
+        keep = (s >= lo) & (s < hi)
+        e, s = e[keep], s[keep]
+        d = torch.searchsorted(indptr, e, right=True) - 1
+        srcs.append(s.to(index_dtype))
+        dsts.append(d.to(index_dtype))
+        del e, s, d, keep
+    return torch.cat(srcs), torch.cat(dsts)
+
+
+def powerlaw_hashed(num_nodes, num_edges, alpha=2.3, max_deg=None, seed=0, device="cpu", index_dtype=torch.int32):
+    """the whole hashed power-law graph as destination-sorted COO (src, dst, num_nodes)"""
+    indptr = powerlaw_indptr(num_nodes, num_edges, alpha, max_deg, seed, device)
+    src, dst = powerlaw_hashed_rows(indptr, num_nodes, 0, num_nodes, seed, index_dtype)
+    return src, dst, num_nodes
+
+
 def arxiv_like(num_nodes=169_343, num_edges=1_166_243, seed=0, device="cpu", bidirected_self_loops=False):
     """power-law in-degree capped at ~13 k (ogbn-arxiv's max in-degree); edge ids shuffled so the COO
     is NOT pre-sorted (the builder must do real work)."""

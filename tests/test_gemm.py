@@ -1,0 +1,67 @@
+"""tcgen05/TMEM/TMA projection kernel (sirgcn_gemm_tn) against a plain PyTorch fp32 reference of the same op.
+Tolerance: the output is rounded to bf16/fp16 once (rel 2^-8 / 2^-11 of the row maximum) on top of fp32
+accumulation of exactly representable 16-bit products, so 1e-2 (bf16) / 2e-3 (fp16) relative to the tensor max."""
+import pytest
+import torch
+
+import sirgcn_b200  # noqa: F401
+from sirgcn_b200 import gemm
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    return (a.float() - b).abs().max().item() / max(b.abs().max().item(), 1e-20)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 1e-2), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("m,n,k", [(128, 256, 128), (1, 16, 8), (127, 128, 64), (300, 256, 128), (1000, 96, 200),
+                                   (4096, 264, 512), (777, 512, 72), (20000, 256, 128), (129, 8, 40)])
+def test_gemm_tn_matches_fp32_reference(dtype, tol, m, n, k):
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k, device=DEV).to(dtype)
+    b = (torch.randn(n, k, device=DEV) / k ** 0.5).to(dtype)
+    bias = torch.randn(n, device=DEV)
+    ref = a.float() @ b.float().t()
+    out = gemm.gemm_tn(a, b)
+    assert out.dtype == dtype and out.shape == (m, n)
+    assert rel(out, ref) < tol
+    out_b = gemm.gemm_tn(a, b, bias)
+    assert rel(out_b, ref + bias) < tol
+
+
+def test_gemm_tn_strided_operands_and_output_view():
+    """Q|K halves and padded tables are strided views: ld > row length"""
+    torch.manual_seed(0)
+    m, n, k = 515, 80, 72
+    abuf = torch.randn(m, 96, device=DEV).to(torch.bfloat16)
+    a = abuf[:, :k]
+    b = (torch.randn(n, k, device=DEV) / 8).to(torch.bfloat16)
+    cbuf = torch.full((m, 128), 7.0, device=DEV, dtype=torch.bfloat16)
+    gemm.gemm_tn(a, b, out=cbuf[:, 8:8 + n])
+    ref = a.float() @ b.float().t()
+    assert rel(cbuf[:, 8:8 + n], ref) < 1e-2
+    assert bool((cbuf[:, :8] == 7).all()) and bool((cbuf[:, 8 + n:] == 7).all())      # nothing outside the view
+
+
+def test_gemm_repeatable_and_layer_uses_it():
+    from torch import nn
+    from sirgcn_b200 import Graph, SIRConv, _lib
+    torch.manual_seed(0)
+    a = torch.randn(5000, 128, device=DEV).to(torch.bfloat16)
+    b = torch.randn(256, 128, device=DEV).to(torch.bfloat16)
+    assert torch.equal(gemm.gemm_tn(a, b), gemm.gemm_tn(a, b))
+    src, dst = torch.randint(0, 500, (4000,), device=DEV), torch.randint(0, 500, (4000,), device=DEV)
+    g = Graph(src, dst, 500)
+    layer = SIRConv(64, 128, 64, nn.ReLU(), agg_type="mean").to(DEV)
+    x = torch.randn(500, 64, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    before = _lib.launch_count()
+    out = layer(g, x)
+    out.backward(torch.randn_like(out))
+    # 2 forward GEMMs + 2 dgrads + 3 edge passes at least
+    assert _lib.launch_count() - before >= 7
+    ref = SIRConv(64, 128, 64, nn.ReLU(), agg_type="mean").to(DEV)
+    ref.load_state_dict(layer.state_dict())
+    out32 = ref(g, x.detach().float())
+    assert rel(out, out32.detach()) < 2e-2

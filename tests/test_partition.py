@@ -1,0 +1,231 @@
+"""Destination-row partition (sir-gcn_b200/partition.py): G ranks == 1 rank.
+
+CPU part (`-m "not gpu"`): world_size-2 gloo run of the host logic (slicing, padding, the three all-gathers,
+weight-gradient all-reduce) with a torch stand-in for the CUDA edge kernels, checked against the CPU oracle on the
+whole graph.  GPU part: the same through the C-ABI kernels (world 1 on one GPU, NCCL world 2 when two are visible).
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch import nn
+
+import sirgcn_b200  # noqa: F401
+from oracle.sirconv_ref import RefGraph, RefSIRConv, csr_csc_ref
+from sirgcn_b200 import SIRConv, _lib, partition
+from sirgcn_b200.graph import CompressedRows
+
+ACTS = {"relu": nn.ReLU, "leaky": lambda: nn.LeakyReLU(0.2), "gelu": nn.GELU}
+
+
+def _act(code, p, z):
+    if code == _lib.ACT_RELU:
+        return torch.relu(z), (z > 0).to(z.dtype)
+    if code == _lib.ACT_LEAKY_RELU:
+        return torch.where(z > 0, z, p * z), torch.where(z > 0, torch.ones_like(z), torch.full_like(z, p))
+    if code == _lib.ACT_GELU:
+        cdf = 0.5 * (1 + torch.erf(z * 0.7071067811865476))
+        pdf = 0.3989422804014327 * torch.exp(-0.5 * z * z)
+        return z * cdf, cdf + z * pdf
+    return z, torch.ones_like(z)
+
+
+class TorchEdgeBackend:
+    """torch restatement of the three edge entry points on CompressedRows (test stand-in for the CUDA kernels)"""
+
+    @staticmethod
+    def _rid(rows):
+        deg = (rows.indptr[1:] - rows.indptr[:-1]).long()
+        return torch.repeat_interleave(torch.arange(rows.n_rows), deg)
+
+    @staticmethod
+    def forward(rows, q, k, e, ds, ss, act, ap):
+        rid, idx = TorchEdgeBackend._rid(rows), rows.idx.long()
+        m, _ = _act(act, ap, q[rid] + k[idx])
+        if ss is not None:
+            m = m * ss[idx].to(m.dtype).unsqueeze(1)
+        out = torch.zeros(rows.n_rows, q.shape[1], dtype=q.dtype).index_add_(0, rid, m)
+        return out if ds is None else out * ds[:rows.n_rows].to(out.dtype).unsqueeze(1)
+
+    @staticmethod
+    def backward_q(rows, q, k, e, da, ds, ss, act, ap, want_de, out=None, scale_da_inplace=False):
+        rid, idx = TorchEdgeBackend._rid(rows), rows.idx.long()
+        _, dact = _act(act, ap, q[rid] + k[idx])
+        g = da[rid] * dact
+        if ds is not None:
+            g = g * ds[:rows.n_rows][rid].to(g.dtype).unsqueeze(1)
+        if ss is not None:
+            g = g * ss[idx].to(g.dtype).unsqueeze(1)
+        out.copy_(torch.zeros(rows.n_rows, q.shape[1], dtype=q.dtype).index_add_(0, rid, g))
+        return out, None
+
+    @staticmethod
+    def backward_k(rows, q, k, e, da, ds, ss, act, ap, out=None):
+        rid, idx = TorchEdgeBackend._rid(rows), rows.idx.long()     # rows = local sources, idx = global destinations
+        _, dact = _act(act, ap, q[idx] + k[rid])
+        g = da[idx] * dact
+        if ds is not None:
+            g = g * ds[idx].to(g.dtype).unsqueeze(1)
+        if ss is not None:
+            g = g * ss[:rows.n_rows][rid].to(g.dtype).unsqueeze(1)
+        out.copy_(torch.zeros(rows.n_rows, k.shape[1], dtype=k.dtype).index_add_(0, rid, g))
+        return out
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _case(seed, n, e, d_in, d, d_out, act, agg, dtype=torch.float64):
+    g = torch.Generator().manual_seed(seed)
+    src, dst = torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)
+    dst[: e // 3] = 2                      # a hub destination
+    torch.manual_seed(seed)
+    layer = RefSIRConv(d_in, d, d_out, ACTS[act](), agg_type=agg).to(dtype)
+    x = torch.randn(n, d_in, dtype=dtype)
+    gout = torch.randn(n, d_out, dtype=dtype)
+    return src, dst, layer, x, gout
+
+
+def _reference(src, dst, n, layer, x, gout):
+    xr = x.clone().requires_grad_(True)
+    out = layer(RefGraph(src, dst, n), xr)
+    grads = torch.autograd.grad(out, [xr] + list(layer.parameters()), gout)
+    return out.detach(), grads
+
+
+def _gloo_worker(rank, world, port, agg, act, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 37                              # not divisible by the world size: padding rows exist
+        src, dst, ref, x, gout = _case(3, n, 400, 6, 12, 5, act, agg)
+        out_ref, g_ref = _reference(src, dst, n, ref, x, gout)
+        c = csr_csc_ref(src, dst, n)
+        csr = CompressedRows(c[0], c[1], None)
+        csc = CompressedRows(c[3], c[4], None)
+        part = partition.RowPartition.from_csr_csc(csr, csc, n, rank, world)
+        layer = SIRConv(6, 12, 5, ACTS[act](), agg_type=agg).double()
+        layer.load_state_dict(ref.state_dict())
+        xl = x[part.lo:part.hi].clone().requires_grad_(True)
+        out = partition.partitioned_sirconv(layer, part, xl, backend=TorchEdgeBackend)
+        grads = torch.autograd.grad(out, [xl] + list(layer.parameters()), gout[part.lo:part.hi])
+        # degree coefficients are fp32 by design (the kernels read fp32 scales): 1e-6; pure sums: 1e-10
+        tol = dict(rtol=1e-10, atol=1e-12) if agg == "sum" else dict(rtol=1e-6, atol=1e-7)
+        ok = torch.allclose(out, out_ref[part.lo:part.hi], **tol)
+        ok &= torch.allclose(grads[0], g_ref[0][part.lo:part.hi], **tol)
+        for a, b in zip(grads[1:], g_ref[1:]):          # every rank holds the FULL-graph weight gradient
+            ok &= torch.allclose(a, b, **tol)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("agg,act", [("sum", "relu"), ("mean", "leaky"), ("sym", "gelu")])
+def test_partition_gloo_world2_matches_single_process(agg, act):
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_gloo_worker, args=(world, port, agg, act, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
+
+
+def test_partition_bounds_cover_every_row_once():
+    for n, world in [(10, 3), (37, 2), (5, 8), (16, 4)]:
+        rows = []
+        for r in range(world):
+            n_pad, lo, hi = partition.RowPartition.bounds(n, r, world)
+            assert hi - lo <= n_pad
+            rows += list(range(lo, hi))
+        assert rows == list(range(n))
+
+
+# ---- GPU ------------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-20)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("agg,act", [("sum", "relu"), ("mean", "relu"), ("sym", "leaky")])
+def test_partition_world1_equals_graph_path(agg, act):
+    from sirgcn_b200 import Graph
+    dev = "cuda:0"
+    src, dst, ref, x, gout = _case(5, 300, 4000, 16, 64, 24, act, agg, torch.float32)
+    g = Graph(src.to(dev), dst.to(dev), 300, long_threshold=64)
+    layer = SIRConv(16, 64, 24, ACTS[act](), agg_type=agg).to(dev)
+    layer.load_state_dict(ref.state_dict())
+    xa = x.to(dev).requires_grad_(True)
+    out_a = layer(g, xa)
+    ga = torch.autograd.grad(out_a, [xa] + list(layer.parameters()), gout.to(dev))
+    part = partition.RowPartition.from_graph(g, 0, 1)
+    xb = x.to(dev).requires_grad_(True)
+    out_b = partition.partitioned_sirconv(layer, part, xb)
+    gb = torch.autograd.grad(out_b, [xb] + list(layer.parameters()), gout.to(dev))
+    assert _rel(out_b, out_a) < 1e-5
+    for a, b in zip(gb, ga):
+        assert _rel(a, b) < 1e-5
+    out_ref, g_ref = _reference(src, dst, 300, ref.double(), x.double(), gout.double())
+    assert _rel(out_b, out_ref) < 1e-5 and _rel(gb[0], g_ref[0]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_partition_from_hashed_generator_matches_whole_graph_slices():
+    from sirgcn_b200 import Graph, synth
+    dev = "cuda:0"
+    n, e, world = 3001, 90000, 4
+    src, dst, _ = synth.powerlaw_hashed(n, e, seed=7, device=dev)
+    g = Graph(src, dst, n, long_threshold=64)
+    for rank in range(world):
+        whole = partition.RowPartition.from_graph(g, rank, world)
+        # (synthetic_powerlaw itself needs a process group for the norm all_gather: build its pieces rank by rank)
+        ip = synth.powerlaw_indptr(n, e, seed=7, device=dev)
+        n_pad, lo, hi = partition.RowPartition.bounds(n, rank, world)
+        in_src, in_dst = synth.powerlaw_hashed_rows(ip, n, lo, hi, seed=7)
+        out_src, out_dst = synth.powerlaw_hashed_cols(ip, n, lo, hi, seed=7, step=20000)
+        csr = partition.build_rows(in_dst - lo, in_src, hi - lo, 64)
+        csc = partition.build_rows(out_src - lo, out_dst, hi - lo, 64)
+        assert torch.equal(csr.indptr, whole.csr.indptr) and torch.equal(csr.idx, whole.csr.idx)
+        assert torch.equal(csc.indptr, whole.csc.indptr) and torch.equal(csc.idx, whole.csc.idx)
+
+
+def _nccl_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from sirgcn_b200 import synth
+        n, e, d = 20011, 600000, 128
+        part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, seed=3, device=dev, long_threshold=64)
+        src, dst, _ = synth.powerlaw_hashed(n, e, seed=3, device="cpu", index_dtype=torch.int64)
+        torch.manual_seed(0)
+        ref = RefSIRConv(d, d, d, nn.ReLU(), agg_type="mean")
+        x, gout = torch.randn(n, d), torch.randn(n, d)
+        out_ref, g_ref = _reference(src, dst, n, ref.double(), x.double(), gout.double())
+        layer = SIRConv(d, d, d, nn.ReLU(), agg_type="mean").to(dev)
+        layer.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+        xl = x[part.lo:part.hi].to(dev).requires_grad_(True)
+        out = partition.partitioned_sirconv(layer, part, xl)
+        grads = torch.autograd.grad(out, [xl] + list(layer.parameters()), gout[part.lo:part.hi].to(dev))
+        errs = [_rel(out, out_ref[part.lo:part.hi]), _rel(grads[0], g_ref[0][part.lo:part.hi])]
+        errs += [_rel(a, b) for a, b in zip(grads[1:], g_ref[1:])]
+        ret[rank] = max(errs)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_partition_nccl_world2():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_nccl_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert len(ret) == 2 and max(ret.values()) < 1e-5, dict(ret)
