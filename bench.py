@@ -36,6 +36,7 @@ os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 import torch  # noqa: E402
 from torch import nn  # noqa: E402
 
+_REAL_STDOUT = None
 METRIC = "sirgcn_conv_fwd_bwd_gedges_per_s"
 UNIT = "Gedges/s"
 
@@ -181,7 +182,13 @@ def run_reference(args, w):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def workload_config(args, w):
@@ -189,7 +196,8 @@ def workload_config(args, w):
     return {"workload": f"{args.workload}: {w['desc']}" + ("" if args.scale == 1 else f" at scale {args.scale:g}"),
             "nodes": n, "edges": e, "d_in": w["d_in"], "d_hidden": w["d"], "layers": w["layers"],
             "agg": w["agg"], "activation": w["act"], "table_dtype": w["dtype"],
-            "partition": "single GPU" if args.gpus == 1 else f"1-D destination rows over {args.gpus} GPUs",
+            "partition": "single GPU" if args.gpus == 1 else
+            f"1-D destination rows over {args.gpus} GPUs, K all-gather in {args.phases} phase(s); Q and dA all-gathers hidden behind the edge walks",
             "l2": "inputs >> 126 MB L2, no flush" if e * w["d"] * (4 if w["dtype"] == "f32" else 2) > (1 << 30)
             else "L2 flushed (256 MiB write) between timed steps"}
 
@@ -243,7 +251,7 @@ def run_gpu(args, w):
     else:
         from sirgcn_b200 import partition
         part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, alpha=2.3, max_deg=w["max_deg"],
-                                                         seed=0, device=dev)
+                                                         seed=0, device=dev, phases=args.phases)
         n_local, e_local = part.n_local, part.num_local_edges
         run_layer = lambda layer, h: partition.partitioned_sirconv(layer, part, h)
     torch.cuda.synchronize()
@@ -305,10 +313,21 @@ def run_gpu(args, w):
         step(x_dev)
     sampler = ClockSampler(local) if rank == 0 else None
     function.EDGE_TIMERS = []
+    if world > 1:
+        partition.PHASE_MARKS = []
     launches0 = _lib.launch_count()
     ms_step = timed(lambda: step(x_dev), args.steps)
     launches = _lib.launch_count() - launches0
     timers, function.EDGE_TIMERS = function.EDGE_TIMERS, None
+    phases = None
+    if world > 1:
+        marks, partition.PHASE_MARKS = partition.PHASE_MARKS, None
+        acc = {}
+        for (l0, e0), (l1, e1) in zip(marks[:-1], marks[1:]):
+            if l1.endswith(":start"):
+                continue
+            acc[l1] = acc.get(l1, 0.0) + e0.elapsed_time(e1)
+        phases = {k: v / args.steps for k, v in acc.items()}      # ms per step (all layers), rank 0
     clocks = sampler.stop() if sampler else None
     peak_mem = torch.cuda.max_memory_allocated() / 2**30
 
@@ -386,14 +405,19 @@ def run_gpu(args, w):
                                      "share_of_step": sum(v[0] for v in per.values()) / (ms_step * args.steps)},
                 "stages": stages},
             "cpu_baseline": cpu,
-            "graph_build_s": t_build, "peak_mem_gib": peak_mem,
+            "graph_build_s": t_build, "peak_mem_gib": peak_mem, "phases_ms_per_step": phases,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # libraries (NCCL's version banner, ...) write to fd 1: keep the real stdout for the ONE JSON line only
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -403,6 +427,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's nodes/edges (debug)")
     ap.add_argument("--cpu-edges", type=int, default=4_000_000, help="edges of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--phases", type=int, default=1, help="N>1: source chunks of the phased K all-gather / forward walk")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIRGCN_ABI_VERSION 3
+#define SIRGCN_ABI_VERSION 5
 
 /* element types of feature tables (accumulation is always fp32) */
 enum { SIRGCN_F32 = 0, SIRGCN_BF16 = 1, SIRGCN_F16 = 2 };
@@ -73,7 +73,11 @@ typedef struct sirgcn_schedule {
     int32_t *long_nchunks; /* [cap_long]   number of chunks of each long row              */
     int32_t *chunk_lrow;   /* [cap_chunks] index into long_rows for each chunk            */
     int32_t *chunk_beg;    /* [cap_chunks] first edge position of each chunk              */
+    int32_t *big_lrows;    /* [cap_big + 1] [0] = number of long rows with more than SIRGCN_BIG_CHUNKS chunks,
+                              then their indices into long_rows (hubs get a whole CTA in the ordered
+                              final sum); cap_big = E / (long_threshold * SIRGCN_BIG_CHUNKS) + 2       */
 } sirgcn_schedule;
+#define SIRGCN_BIG_CHUNKS 32
 
 int sirgcn_csr_build(const int32_t *src, const int32_t *dst, int64_t num_edges, int32_t num_nodes,
                      int32_t *indptr_in, int32_t *col_src, int32_t *eid_in,
@@ -159,6 +163,8 @@ typedef struct sirgcn_edge_args {
     /* work tiles of THIS walk (sirgcn_tiles_build): tile t = rows [tile_row[t], tile_row[t+1]) */
     const int32_t *tile_row; /* [n_tiles + 1]                                            */
     int32_t n_tiles;
+    int32_t accumulate;     /* != 0: out[row] += result instead of out[row] = result (a row's edges split
+                               over several walks, e.g. one walk per arrived source block; fixed order)  */
 } sirgcn_edge_args;
 
 /* bytes of fp32 scratch needed for `partial` */
@@ -181,6 +187,12 @@ int sirgcn_edge_bwd_k(const sirgcn_edge_args *args, void *stream);
  * no IEEE-fp32 MMA; the fp32 parity target is 1e-5). */
 int sirgcn_gemm_tn(const void *a, int64_t lda, const void *b, int64_t ldb, void *c, int64_t ldc,
                    const float *bias, int64_t m, int32_t n, int32_t k, int32_t dtype, void *stream);
+
+/* out[c] = sum over rows of x[r, c] in fp32 (bias gradients of nn.Linear: db_Q, db_R).
+ * n must be a multiple of 16/sizeof(elem) and at most 256 vectors wide; two fixed-order stages. */
+size_t sirgcn_colsum_workspace_bytes(int32_t n);
+int sirgcn_colsum(const void *x, int64_t ld, int64_t m, int32_t n, int32_t dtype, float *out, void *workspace,
+                  size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Split path for arbitrary (non-elementwise) σ, agg_type 'max'/'min', and the

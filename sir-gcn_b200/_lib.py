@@ -21,13 +21,13 @@ EXPORTS = (
     "sirgcn_csr_build_workspace_bytes", "sirgcn_csr_build", "sirgcn_schedule_build",
     "sirgcn_num_tiles", "sirgcn_tiles_build", "sirgcn_rows_build_workspace_bytes", "sirgcn_rows_build",
     "sirgcn_edge_partial_bytes", "sirgcn_edge_fwd", "sirgcn_edge_bwd_q", "sirgcn_edge_bwd_k",
-    "sirgcn_gemm_tn", "sirgcn_gather_add", "sirgcn_segment_sum", "sirgcn_segment_minmax", "sirgcn_segment_minmax_bwd",
+    "sirgcn_gemm_tn", "sirgcn_colsum_workspace_bytes", "sirgcn_colsum", "sirgcn_gather_add", "sirgcn_segment_sum", "sirgcn_segment_minmax", "sirgcn_segment_minmax_bwd",
 )
 
 
 class Schedule(C.Structure):
     _fields_ = [("long_rows", C.c_void_p), ("long_first", C.c_void_p), ("long_nchunks", C.c_void_p),
-                ("chunk_lrow", C.c_void_p), ("chunk_beg", C.c_void_p)]
+                ("chunk_lrow", C.c_void_p), ("chunk_beg", C.c_void_p), ("big_lrows", C.c_void_p)]
 
 
 class EdgeArgs(C.Structure):
@@ -45,7 +45,7 @@ class EdgeArgs(C.Structure):
         ("dst_scale", C.c_void_p), ("src_scale", C.c_void_p),
         ("sched", Schedule), ("n_long", C.c_int32), ("n_chunks", C.c_int32),
         ("partial", C.c_void_p),
-        ("tile_row", C.c_void_p), ("n_tiles", C.c_int32),
+        ("tile_row", C.c_void_p), ("n_tiles", C.c_int32), ("accumulate", C.c_int32),
     ]
 
 
@@ -67,6 +67,8 @@ def lib():
         l.sirgcn_csr_build_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
         l.sirgcn_rows_build_workspace_bytes.restype = C.c_size_t
         l.sirgcn_rows_build_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+        l.sirgcn_colsum_workspace_bytes.restype = C.c_size_t
+        l.sirgcn_colsum_workspace_bytes.argtypes = [C.c_int32]
         l.sirgcn_num_tiles.restype = C.c_int64
         l.sirgcn_num_tiles.argtypes = [C.c_int32, C.c_int64]
         l.sirgcn_edge_partial_bytes.restype = C.c_size_t

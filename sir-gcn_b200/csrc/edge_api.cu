@@ -50,7 +50,7 @@ int validate(const sirgcn_edge_args *a, int mode) {
     if (a->n_chunks > 0) {
         SIRGCN_CHECK_ARG(a->partial && aligned16(a->partial), "partial scratch missing / misaligned");
         SIRGCN_CHECK_ARG(a->sched.long_rows && a->sched.long_first && a->sched.long_nchunks &&
-                             a->sched.chunk_lrow && a->sched.chunk_beg, "schedule arrays missing");
+                             a->sched.chunk_lrow && a->sched.chunk_beg && a->sched.big_lrows, "schedule arrays missing");
     }
     return SIRGCN_OK;
 }

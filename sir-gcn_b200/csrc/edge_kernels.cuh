@@ -450,6 +450,8 @@ __global__ void __launch_bounds__(kWarps * 32, SIRGCN_MIN_CTAS) edge_walk_kernel
                         if (!vok[v]) continue;
 #pragma unroll
                         for (int i = 0; i < NE; ++i) acc[v][i] *= os;
+                        if (a.accumulate)      // phased walks over source blocks (partition.py): out += this block
+                            add_vec<T>(*reinterpret_cast<const uint4 *>(o + v * vstride), acc[v], acc[v]);
                         stg_vec(o + v * vstride, pack<T>(acc[v]));
                     }
                 }
@@ -470,39 +472,54 @@ __global__ void __launch_bounds__(kWarps * 32, SIRGCN_MIN_CTAS) edge_walk_kernel
     }
 }
 
-// ---- one CTA per long row: ordered sum of its partials ---------------------------------------
-// warp w sums chunks first+w, first+w+8, ... in order; warps are then combined in warp order.
+// ---- long rows: ordered sum of the chunk partials -------------------------------------------------
+// One WARP per long row (a power-law graph has tens of thousands of rows just above the threshold with a
+// handful of chunks each): lane l owns 16-byte vectors l, l+32, ...; chunks are summed in chunk order with
+// four interleaved accumulators (ch mod 4), combined in a fixed order => bitwise repeatable.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) edge_long_finalize_kernel(const sirgcn_edge_args a) {
     constexpr int NE = VecTraits<T>::N;
-    extern __shared__ float smem[];  // [8][nvec*NE]
-    const int lrow = blockIdx.x;
+    const int lrow = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (lrow >= a.n_long) return;
+    const int lane = threadIdx.x & 31;
     const int row = a.sched.long_rows[lrow];
     const int first = a.sched.long_first[lrow];
     const int nch = a.sched.long_nchunks[lrow];
+    if (nch > SIRGCN_BIG_CHUNKS) return;                 // hubs: edge_big_finalize_kernel
     const int nvec = (a.d * (int)sizeof(T) + 15) / 16;
     const int width = nvec * NE;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    for (int col = lane; col < width; col += 32) {
-        float s = 0.f;
-        for (int ch = warp; ch < nch; ch += 8) s += a.partial[(int64_t)(first + ch) * width + col];
-        smem[warp * width + col] = s;
-    }
-    __syncthreads();
     float rs = 1.f;
     if (MODE == kFwd && a.dst_scale) rs = a.dst_scale[row];
     if (MODE == kBwdK && a.src_scale) rs = a.src_scale[row];
     T *o = reinterpret_cast<T *>(a.out) + (int64_t)row * a.ldo;
-    for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+    for (int vi = lane; vi < nvec; vi += 32) {
+        float s[4][NE];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < NE; ++i) s[j][i] = 0.f;
+        const float *p = a.partial + (int64_t)first * width + vi * NE;
+        int ch = 0;
+        for (; ch + 4 <= nch; ch += 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < NE; i += 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(p + (int64_t)(ch + j) * width + i);
+                    s[j][i] += t.x; s[j][i + 1] += t.y; s[j][i + 2] += t.z; s[j][i + 3] += t.w;
+                }
+        }
+        for (int j = 0; ch < nch; ++ch, ++j) {
+#pragma unroll
+            for (int i = 0; i < NE; i += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(p + (int64_t)ch * width + i);
+                s[j][i] += t.x; s[j][i + 1] += t.y; s[j][i + 2] += t.z; s[j][i + 3] += t.w;
+            }
+        }
         float r[NE];
 #pragma unroll
-        for (int i = 0; i < NE; ++i) {
-            float s = 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) s += smem[w * width + vi * NE + i];
-            r[i] = s * rs;
-        }
+        for (int i = 0; i < NE; ++i) r[i] = ((s[0][i] + s[1][i]) + (s[2][i] + s[3][i])) * rs;
+        if (a.accumulate) add_vec<T>(*reinterpret_cast<const uint4 *>(o + vi * NE), r, r);
         stg_vec(o + vi * NE, pack<T>(r));
         if (MODE == kBwdQ && a.da_scaled) {      // dA[row] * dst_scale[row] for the CSC walk (may alias dA: all chunks are done)
             const float ds = a.dst_scale ? a.dst_scale[row] : 1.f;
@@ -515,10 +532,76 @@ __global__ void __launch_bounds__(256) edge_long_finalize_kernel(const sirgcn_ed
     }
 }
 
+// Hubs (more than SIRGCN_BIG_CHUNKS chunks): one CTA per row, taken from the schedule's big list by a
+// fixed-size grid.  Warp w sums chunks w, w+8, ... with four interleaved accumulators over float4 columns;
+// the 8 warps are combined in warp order through shared memory => fixed order, bitwise repeatable.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) edge_big_finalize_kernel(const sirgcn_edge_args a) {
+    constexpr int NE = VecTraits<T>::N;
+    extern __shared__ float smem[];                      // [8][width]
+    const int n_big = a.sched.big_lrows[0];
+    const int nvec = (a.d * (int)sizeof(T) + 15) / 16;
+    const int width = nvec * NE, w4 = width / 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = blockIdx.x; b < n_big; b += gridDim.x) {
+        const int lrow = a.sched.big_lrows[1 + b];
+        const int row = a.sched.long_rows[lrow];
+        const int first = a.sched.long_first[lrow];
+        const int nch = a.sched.long_nchunks[lrow];
+        const float4 *p = reinterpret_cast<const float4 *>(a.partial + (int64_t)first * width);
+        for (int c4 = lane; c4 < w4; c4 += 32) {
+            float4 s[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int ch = warp;
+            for (; ch + 24 < nch; ch += 32) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t = p[(int64_t)(ch + 8 * j) * w4 + c4];
+                    s[j].x += t.x; s[j].y += t.y; s[j].z += t.z; s[j].w += t.w;
+                }
+            }
+            for (int j = 0; ch < nch; ch += 8, ++j) {
+                const float4 t = p[(int64_t)ch * w4 + c4];
+                s[j].x += t.x; s[j].y += t.y; s[j].z += t.z; s[j].w += t.w;
+            }
+            float4 r;
+            r.x = (s[0].x + s[1].x) + (s[2].x + s[3].x); r.y = (s[0].y + s[1].y) + (s[2].y + s[3].y);
+            r.z = (s[0].z + s[1].z) + (s[2].z + s[3].z); r.w = (s[0].w + s[1].w) + (s[2].w + s[3].w);
+            reinterpret_cast<float4 *>(smem + warp * width)[c4] = r;
+        }
+        __syncthreads();
+        float rs = 1.f;
+        if (MODE == kFwd && a.dst_scale) rs = a.dst_scale[row];
+        if (MODE == kBwdK && a.src_scale) rs = a.src_scale[row];
+        T *o = reinterpret_cast<T *>(a.out) + (int64_t)row * a.ldo;
+        for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+            float r[NE];
+#pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += smem[w * width + vi * NE + i];
+                r[i] = s * rs;
+            }
+            if (a.accumulate) add_vec<T>(*reinterpret_cast<const uint4 *>(o + vi * NE), r, r);
+            stg_vec(o + vi * NE, pack<T>(r));
+            if (MODE == kBwdQ && a.da_scaled) {
+                const float ds = a.dst_scale ? a.dst_scale[row] : 1.f;
+                float g[NE];
+                unpack<T>(ldg_keep(reinterpret_cast<const T *>(a.da) + (int64_t)row * a.lda + vi * NE), g);
+#pragma unroll
+                for (int i = 0; i < NE; ++i) g[i] *= ds;
+                stg_vec(reinterpret_cast<T *>(a.da_scaled) + (int64_t)row * a.ldds + vi * NE, pack<T>(g));
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T, int VPL, int MODE, bool HAS_E, int ACT, bool GS>
 int launch_gs(const sirgcn_edge_args &a, cudaStream_t st) {
     using C = Cfg<T, VPL, MODE, HAS_E, GS>;
-    constexpr int NE = VecTraits<T>::N;
     const int nvec = (a.d * (int)sizeof(T) + 15) / 16;
     const int NG = 32 / lanes_per_row(nvec, VPL);
     const int B = NG * std::min(C::U, 32 / NG);
@@ -536,9 +619,13 @@ int launch_gs(const sirgcn_edge_args &a, cudaStream_t st) {
     if (a.n_chunks > 0) {
         kern<<<(unsigned)((a.n_chunks + kWarps - 1) / kWarps), kWarps * 32, smem, st>>>(a, 1);
         SIRGCN_LAUNCHED();
-        const size_t fsmem = (size_t)8 * nvec * NE * sizeof(float);
-        edge_long_finalize_kernel<T, MODE><<<(unsigned)a.n_long, 256, fsmem, st>>>(a);
+        edge_long_finalize_kernel<T, MODE><<<(unsigned)((a.n_long + 7) / 8), 256, 0, st>>>(a);
         SIRGCN_LAUNCHED();
+        const int big_grid = std::min(a.n_chunks / SIRGCN_BIG_CHUNKS, kNumSMs * 4);   // n_big <= n_chunks / 33
+        if (big_grid > 0) {
+            edge_big_finalize_kernel<T, MODE><<<big_grid, 256, (size_t)8 * nvec * VecTraits<T>::N * sizeof(float), st>>>(a);
+            SIRGCN_LAUNCHED();
+        }
     }
     return SIRGCN_OK;
 }

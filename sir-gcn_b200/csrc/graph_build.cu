@@ -86,6 +86,7 @@ __global__ void schedule_kernel(const int32_t *__restrict__ indptr, int32_t num_
         s.long_rows[l] = row;
         s.long_first[l] = first;
         s.long_nchunks[l] = nch;
+        if (nch > SIRGCN_BIG_CHUNKS) s.big_lrows[1 + atomicAdd(&s.big_lrows[0], 1)] = l;
         for (int ch = 0; ch < nch; ++ch) {
             s.chunk_lrow[first + ch] = l;
             s.chunk_beg[first + ch] = beg + ch * thr;
@@ -154,7 +155,7 @@ int build_one(const int32_t *key, const int32_t *other, int64_t E, int32_t N, in
 }
 
 int check_sched(const sirgcn_schedule *s) {
-    SIRGCN_CHECK_ARG(s && s->long_rows && s->long_first && s->long_nchunks && s->chunk_lrow && s->chunk_beg,
+    SIRGCN_CHECK_ARG(s && s->long_rows && s->long_first && s->long_nchunks && s->chunk_lrow && s->chunk_beg && s->big_lrows,
                      "schedule arrays missing");
     return SIRGCN_OK;
 }
@@ -203,6 +204,7 @@ int sirgcn_schedule_build(const int32_t *indptr, int32_t num_rows, int32_t long_
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     SIRGCN_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), st));
+    SIRGCN_CUDA(cudaMemsetAsync(sched->big_lrows, 0, sizeof(int32_t), st));
     if (num_rows > 0) {
         schedule_kernel<<<std::min(blocks_for(num_rows), (unsigned)kNumSMs * 16), kThreads, 0, st>>>(
             indptr, num_rows, long_threshold, *sched, counts);

@@ -60,7 +60,7 @@ EDGE_TIMERS = None
 
 
 def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da, e, out, de,
-               dst_scale, src_scale, da_scaled=None):
+               dst_scale, src_scale, da_scaled=None, accumulate=False):
     if not (rows.indptr.is_cuda and q.is_cuda and k.is_cuda and out.is_cuda):
         raise RuntimeError("SIR-GCN edge kernels need CUDA tensors (no CPU fallback)")
     a = _lib.EdgeArgs()
@@ -88,6 +88,7 @@ def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da
     a.partial = None if partial is None else partial.data_ptr()
     a.tile_row = None if rows.tile_row is None else rows.tile_row.data_ptr()
     a.n_tiles = rows.n_tiles
+    a.accumulate = 1 if accumulate else 0
     dev = rows.indptr.device
     with torch.cuda.device(dev):
         if EDGE_TIMERS is not None:
@@ -100,13 +101,15 @@ def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da
     _lib.check(rc, fn_name)
 
 
-def edge_forward(csr: CompressedRows, q, k, e, dst_scale, src_scale, act, act_param):
-    """A = fused edge stage over the rows of `csr` (q indexed by row, k by csr.idx)."""
+def edge_forward(csr: CompressedRows, q, k, e, dst_scale, src_scale, act, act_param, out=None, accumulate=False):
+    """A = fused edge stage over the rows of `csr` (q indexed by row, k by csr.idx); with `accumulate`,
+    `out` (+)= the result — one walk per source block of a phased, partitioned forward."""
     d = q.shape[1]
-    out = _alloc_table(csr.n_rows, d, q.dtype, q.device)
+    if out is None:
+        out = _alloc_table(csr.n_rows, d, q.dtype, q.device)
     if csr.n_rows:
         _edge_call("sirgcn_edge_fwd", csr, d, q.dtype, act, act_param, q, k, None, e, out, None,
-                   dst_scale, src_scale)
+                   dst_scale, src_scale, accumulate=accumulate)
     out._sirgcn_padded = True
     return out
 
@@ -220,7 +223,7 @@ class SIRLayerFunction(torch.autograd.Function):
         gout = gout.to(qk.dtype)
         gout = gout if gout.stride(-1) == 1 else gout.contiguous()
         dw_r = gemm.linear_wgrad(gout, a, w_r.dtype) if need[4] else None
-        db_r = gout.sum(0).to(w_r.dtype) if (need[5] and ctx.has_bias[1]) else None
+        db_r = gemm.column_sum(gout, w_r.dtype) if (need[5] and ctx.has_bias[1]) else None
         da = gemm.linear_dgrad(gout, w_r.to(qk.dtype), pad_to=_pad_cols(d, qk.dtype))[:, :d]   # [N, d]
         da._sirgcn_padded = True
         ds, ss = g.scales(ctx.agg_type)
@@ -232,7 +235,7 @@ class SIRLayerFunction(torch.autograd.Function):
         edge_backward_k(g.csc, q, k, e, da, None, ss, ctx.act, ctx.act_param, out=dk)
         del da
         dw_qk = gemm.linear_wgrad(dqk, feat, w_qk.dtype) if need[1] else None
-        db_qk = dqk.sum(0).to(w_qk.dtype) if (need[2] and ctx.has_bias[0]) else None
+        db_qk = gemm.column_sum(dqk, w_qk.dtype) if (need[2] and ctx.has_bias[0]) else None
         dfeat = gemm.linear_dgrad(dqk, w_qk.to(qk.dtype)).to(feat.dtype) if need[0] else None
         return dfeat, dw_qk, db_qk, de, dw_r, db_r, None, None, None, None, None, None
 

@@ -59,12 +59,31 @@ def gemm_tn(a, b, bias=None, out=None):
     return out
 
 
+def column_sum(x, out_dtype=torch.float32):
+    """Σ_rows x in fp32 (bias gradients): sirgcn_colsum on CUDA tables with 16-byte rows, torch elsewhere"""
+    es = x.element_size()
+    n = x.shape[1]
+    if (x.is_cuda and x.dtype in _lib.DTYPE_CODE and x.dim() == 2 and x.stride(1) == 1 and x.data_ptr() % 16 == 0
+            and (n * es) % 16 == 0 and (n * es) // 16 <= 256 and (x.shape[0] <= 1 or (x.stride(0) * es) % 16 == 0)):
+        L = _lib.lib()
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+        nbytes = L.sirgcn_colsum_workspace_bytes(C.c_int32(n))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = L.sirgcn_colsum(_lib.ptr(x), C.c_int64(_ld(x)), C.c_int64(x.shape[0]), C.c_int32(n),
+                                 C.c_int32(_lib.DTYPE_CODE[x.dtype]), _lib.ptr(out), _lib.ptr(ws), C.c_size_t(nbytes),
+                                 _lib.stream_ptr(x.device))
+        _lib.check(rc, "sirgcn_colsum")
+        return out.to(out_dtype)
+    return x.sum(0, dtype=torch.float64 if x.dtype == torch.float64 else torch.float32).to(out_dtype)
+
+
 def linear(x, weight, bias=None):
     """autograd-visible projection used by the composed (dropout / split) paths"""
     return F.linear(x, weight, bias)
 
 
-def linear_forward(x, weight, bias):
+def linear_forward(x, weight, bias, out=None):
     """no-autograd forward used inside SIRLayerFunction; output dtype follows autocast / x"""
     if torch.is_autocast_enabled("cuda"):
         dt = torch.get_autocast_dtype("cuda")
@@ -73,13 +92,18 @@ def linear_forward(x, weight, bias):
     elif weight.dtype != x.dtype:
         weight = weight.to(x.dtype)
     if x.dim() == 2 and tc_eligible(x, weight.shape[0], weight.shape[1]):
-        return gemm_tn(x, weight.detach(), bias)
-    return F.linear(x, weight, None if bias is None else bias.to(x.dtype))
+        return gemm_tn(x, weight.detach(), bias, out=out)
+    res = F.linear(x, weight, None if bias is None else bias.to(x.dtype))
+    return res if out is None else out.copy_(res)
 
 
-def linear_dgrad(dy, weight, pad_to=None):
+def linear_dgrad(dy, weight, pad_to=None, out=None):
     """dX = dY · W; with pad_to, the result is a [M, pad_to] buffer whose extra columns are zero"""
     k = weight.shape[1]
+    if out is not None:
+        if dy.dim() == 2 and tc_eligible(dy, k, weight.shape[0]):
+            return gemm_tn(dy, weight.detach().t().contiguous(), out=out)
+        return out.copy_(dy @ weight)
     if dy.dim() == 2 and tc_eligible(dy, k, weight.shape[0]):
         wt = weight.detach().t().contiguous()               # [in, out]: K-major B operand of the TN kernel (tiny)
         if pad_to is None or pad_to == k:

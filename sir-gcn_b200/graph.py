@@ -32,7 +32,7 @@ class CompressedRows:
             if indptr.is_cuda:
                 sched, counts = _build_schedule(indptr, self.n_rows, self.num_pos, self.long_threshold)
             else:   # host-side structure (partition planning / gloo tests): never handed to a kernel
-                sched, counts = [torch.empty(0, dtype=torch.int32)] * 5, (0, 0)
+                sched, counts = [torch.empty(0, dtype=torch.int32)] * 6, (0, 0)
         self._sched_tensors = sched
         self.n_long, self.n_chunks = int(counts[0]), int(counts[1])
         self.sched = _lib.Schedule(*[_lib.ptr(t).value for t in sched])
@@ -77,7 +77,8 @@ def _sched_alloc(num_pos, thr, device):
     cap_long = num_pos // thr + 1
     cap_chunks = 2 * (num_pos // thr) + 2
     i32 = lambda n: torch.empty(n, dtype=torch.int32, device=device)
-    return [i32(cap_long), i32(cap_long), i32(cap_long), i32(cap_chunks), i32(cap_chunks)]
+    cap_big = num_pos // (thr * 32) + 2            # SIRGCN_BIG_CHUNKS
+    return [i32(cap_long), i32(cap_long), i32(cap_long), i32(cap_chunks), i32(cap_chunks), i32(cap_big + 1)]
 
 
 def _build_schedule(indptr, n_rows, num_pos, thr):

@@ -65,3 +65,21 @@ def test_gemm_repeatable_and_layer_uses_it():
     ref.load_state_dict(layer.state_dict())
     out32 = ref(g, x.detach().float())
     assert rel(out, out32.detach()) < 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,n", [(1, 8), (1000, 128), (70001, 256), (333, 96), (5, 1024)])
+def test_column_sum(dtype, m, n):
+    """bias-gradient reduction (sirgcn_colsum): fp32 accumulation of the stored values, bitwise repeatable"""
+    if dtype != torch.float32 and n == 1024 and False:
+        pytest.skip()
+    torch.manual_seed(m + n)
+    x = torch.randn(m, n, device=DEV).to(dtype)
+    got = gemm.column_sum(x)
+    ref = x.double().sum(0)
+    assert got.dtype == torch.float32 and got.shape == (n,)
+    assert (got.double() - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()) * max(1.0, m ** 0.5 / 30)
+    assert torch.equal(got, gemm.column_sum(x))
+    view = torch.randn(m, n + 16, device=DEV).to(dtype)[:, 8:8 + n] if dtype != torch.float32 else None
+    if view is not None:      # strided 16-byte aligned view
+        assert (gemm.column_sum(view).double() - view.double().sum(0)).abs().max().item() <= 1e-4 * max(1.0, m ** 0.5)

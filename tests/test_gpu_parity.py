@@ -59,7 +59,9 @@ def test_csr_build_bit_exact(n, e, seed):
         long_rows = torch.nonzero(deg > 64).flatten()
         assert rows.n_long == long_rows.numel()
         assert rows.n_chunks == int(((deg[long_rows] + 63) // 64).sum())
-        lr, lf, ln, cl, cb = [t.cpu() for t in rows._sched_tensors]
+        lr, lf, ln, cl, cb, big = [t.cpu() for t in rows._sched_tensors]
+        want_big = sorted(i for i in range(rows.n_long) if int(ln[i]) > 32)
+        assert int(big[0]) == len(want_big) and sorted(big[1:1 + len(want_big)].tolist()) == want_big
         assert sorted(lr[: rows.n_long].tolist()) == long_rows.tolist()
         for i in range(rows.n_long):
             r, first, nch = int(lr[i]), int(lf[i]), int(ln[i])

@@ -42,13 +42,17 @@ class TorchEdgeBackend:
         return torch.repeat_interleave(torch.arange(rows.n_rows), deg)
 
     @staticmethod
-    def forward(rows, q, k, e, ds, ss, act, ap):
+    def forward(rows, q, k, e, ds, ss, act, ap, out=None, accumulate=False):
         rid, idx = TorchEdgeBackend._rid(rows), rows.idx.long()
         m, _ = _act(act, ap, q[rid] + k[idx])
         if ss is not None:
             m = m * ss[idx].to(m.dtype).unsqueeze(1)
-        out = torch.zeros(rows.n_rows, q.shape[1], dtype=q.dtype).index_add_(0, rid, m)
-        return out if ds is None else out * ds[:rows.n_rows].to(out.dtype).unsqueeze(1)
+        res = torch.zeros(rows.n_rows, q.shape[1], dtype=q.dtype).index_add_(0, rid, m)
+        if ds is not None:
+            res = res * ds[:rows.n_rows].to(res.dtype).unsqueeze(1)
+        if out is None:
+            return res
+        return out.add_(res) if accumulate else out.copy_(res)
 
     @staticmethod
     def backward_q(rows, q, k, e, da, ds, ss, act, ap, want_de, out=None, scale_da_inplace=False):
@@ -99,7 +103,7 @@ def _reference(src, dst, n, layer, x, gout):
     return out.detach(), grads
 
 
-def _gloo_worker(rank, world, port, agg, act, ret):
+def _gloo_worker(rank, world, port, agg, act, phases, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -109,7 +113,8 @@ def _gloo_worker(rank, world, port, agg, act, ret):
         c = csr_csc_ref(src, dst, n)
         csr = CompressedRows(c[0], c[1], None)
         csc = CompressedRows(c[3], c[4], None)
-        part = partition.RowPartition.from_csr_csc(csr, csc, n, rank, world)
+        part = partition.RowPartition.from_csr_csc(csr, csc, n, rank, world, phases=phases)
+        assert len(part.csr_phase) == phases and sum(c.num_pos for c in part.csr_phase) == part.csr.num_pos
         layer = SIRConv(6, 12, 5, ACTS[act](), agg_type=agg).double()
         layer.load_state_dict(ref.state_dict())
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
@@ -126,12 +131,12 @@ def _gloo_worker(rank, world, port, agg, act, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("agg,act", [("sum", "relu"), ("mean", "leaky"), ("sym", "gelu")])
-def test_partition_gloo_world2_matches_single_process(agg, act):
+@pytest.mark.parametrize("agg,act,phases", [("sum", "relu", 1), ("mean", "leaky", 2), ("sym", "gelu", 3)])
+def test_partition_gloo_world2_matches_single_process(agg, act, phases):
     world, port = 2, _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_gloo_worker, args=(world, port, agg, act, ret), nprocs=world, join=True)
+        mp.spawn(_gloo_worker, args=(world, port, agg, act, phases, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
 
 
@@ -202,20 +207,25 @@ def _nccl_worker(rank, world, port, ret):
     try:
         from sirgcn_b200 import synth
         n, e, d = 20011, 600000, 128
-        part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, seed=3, device=dev, long_threshold=64)
-        src, dst, _ = synth.powerlaw_hashed(n, e, seed=3, device="cpu", index_dtype=torch.int64)
+        part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, seed=3, device=dev, long_threshold=64,
+                                                         phases=2)
+        # same device as the partition: the degree law is drawn with the device's RNG
+        src, dst, _ = synth.powerlaw_hashed(n, e, seed=3, device=dev, index_dtype=torch.int64)
+        src, dst = src.cpu(), dst.cpu()
         torch.manual_seed(0)
-        ref = RefSIRConv(d, d, d, nn.ReLU(), agg_type="mean")
+        # a smooth σ: with ReLU/LeakyReLU the fp32-vs-fp64 comparison at this size (77 M pre-activations) is dominated
+        # by σ' flipping for the handful of |z| < 1e-7 elements, not by arithmetic error
+        ref = RefSIRConv(d, d, d, nn.GELU(), agg_type="mean")
         x, gout = torch.randn(n, d), torch.randn(n, d)
         out_ref, g_ref = _reference(src, dst, n, ref.double(), x.double(), gout.double())
-        layer = SIRConv(d, d, d, nn.ReLU(), agg_type="mean").to(dev)
+        layer = SIRConv(d, d, d, nn.GELU(), agg_type="mean").to(dev)
         layer.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
         xl = x[part.lo:part.hi].to(dev).requires_grad_(True)
         out = partition.partitioned_sirconv(layer, part, xl)
         grads = torch.autograd.grad(out, [xl] + list(layer.parameters()), gout[part.lo:part.hi].to(dev))
         errs = [_rel(out, out_ref[part.lo:part.hi]), _rel(grads[0], g_ref[0][part.lo:part.hi])]
         errs += [_rel(a, b) for a, b in zip(grads[1:], g_ref[1:])]
-        ret[rank] = max(errs)
+        ret[rank] = [float(f"{x:.3e}") for x in errs]      # out, dfeat, dW_Q, db_Q, dW_K, dW_R, db_R
     finally:
         dist.destroy_process_group()
 
@@ -228,4 +238,4 @@ def test_partition_nccl_world2():
     with mp.Manager() as mgr:
         ret = mgr.dict()
         mp.spawn(_nccl_worker, args=(world, port, ret), nprocs=world, join=True)
-        assert len(ret) == 2 and max(ret.values()) < 1e-5, dict(ret)
+        assert len(ret) == 2 and max(max(v) for v in ret.values()) < 1e-5, dict(ret)
