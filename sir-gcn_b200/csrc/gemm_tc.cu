@@ -7,12 +7,13 @@
 //     dgrad    dH    = dY · W = dY · (W^T)^T              (B = W^T, a tiny host-side transpose)
 //
 // Structure (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles of A (128 x 64) and B (BN x 64) into a 4-stage
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles of A (128 x 64) and B (BN x 64) into a 3-stage
 //            128B-swizzled shared-memory ring, completion on mbarriers (expect_tx)
 //   warp 1   allocates TMEM, issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN<=256, K=16) from one
 //            elected lane; tcgen05.commit releases ring slots and publishes finished accumulators
-//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> +bias -> bf16/fp16 -> 64-byte row
-//            segments to global; two TMEM accumulator stages let tile i+1's MMAs overlap tile i's epilogue
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> +bias -> bf16/fp16 -> 128B-swizzled
+//            staging tile in shared memory -> cp.async.bulk.tensor store (coalesced, clips the M/N tails);
+//            two TMEM accumulator stages let tile i+1's MMAs overlap tile i's epilogue
 // These GEMMs are skinny (K = d_in <= 512, N = 2d or d_out): they sit at the memory/compute ridge
 // (DESIGN.md §2.4), so the tile is chosen to read A once and write C once; B is L2-resident.
 #include <cuda.h>
@@ -24,13 +25,15 @@ namespace {
 
 constexpr int kBM = 128;          // rows of C per tile = UMMA_M
 constexpr int kBK = 64;           // K elements per ring stage (= one 128-byte swizzle row of 16-bit elements)
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kMaxBN = 256;
 constexpr int kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kBBytes = kMaxBN * kBK * 2;     // 32 KB (box may be smaller)
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kGemmThreads = 192;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int kCBoxBytes = kBM * 64 * 2;      // one 128 x 64 output box (128-byte swizzled rows) = 16 KB
+constexpr int kCBytes = (kMaxBN / 64) * kCBoxBytes;   // output staging for the TMA store: 64 KB
+constexpr int kSmemBytes = kStages * kStageBytes + kCBytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment slack*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -55,6 +58,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -117,11 +123,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 template <bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               void *__restrict__ c, int64_t ldc, const float *__restrict__ bias, int M, int N, int K, int bn) {
+               const __grid_constant__ CUtensorMap map_c, const float *__restrict__ bias, int M, int N, int K, int bn) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    float *s_bias = reinterpret_cast<float *>(smem + kStages * kStageBytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes + 1024);
+    unsigned char *s_c = smem + kStages * kStageBytes;                   // 1024-byte aligned output staging
+    float *s_bias = reinterpret_cast<float *>(s_c + kCBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_c + kCBytes + 1024);
     // bars: full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4), then the TMEM base word
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
     const uint32_t bar0 = smem_u32(bars);
@@ -133,8 +140,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + bn - 1) / bn;
     const int tiles = m_tiles * n_tiles, kblocks = (K + kBK - 1) / kBK;
+    const int bnp = (bn + 31) & ~31;                  // accumulator stage stride: the epilogue reads 32-column groups
     int tmem_cols = 32;
-    while (tmem_cols < 2 * bn) tmem_cols <<= 1;
+    while (tmem_cols < 2 * bnp) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -148,6 +156,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     }
     if (warp == 1) {   // TMEM allocation: one full warp, address lands in shared memory
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
@@ -185,7 +194,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
                 mbar_wait(tempty_bar(as), aphase ^ 1);          // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(as * bn);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * bnp);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);          // TMA bytes have landed
                     tc_fence_after();
@@ -211,40 +220,49 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * bn;
             if (bias != nullptr && n0 != bias_n0) {             // stage this column block's bias once
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int j = threadIdx.x - 64; j < bn; j += 128) s_bias[j] = (n0 + j < N) ? bias[n0 + j] : 0.f;
+                for (int j = threadIdx.x - 64; j < bnp; j += 128) s_bias[j] = (j < bn && n0 + j < N) ? bias[n0 + j] : 0.f;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 bias_n0 = n0;
             }
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
-            const int row = m0 + q * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bn);
-            unsigned char *crow = reinterpret_cast<unsigned char *>(c) + ((int64_t)row * ldc + n0) * 2;
-            for (int c0 = 0; c0 < bn; c0 += 32) {
+            // the previous tile's TMA store must have finished reading the staging tile
+            if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int r = q * 32 + lane;                        // row inside the tile = TMEM lane
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bnp);
+            const uint32_t srow = smem_u32(s_c) + (uint32_t)r * 128u;
+            for (int c0 = 0; c0 < bnp; c0 += 32) {
                 uint32_t v[32];
                 tc_ld32(taddr + (uint32_t)c0, v);
                 tc_wait_ld();
-                if (row < M) {
+                const uint32_t box = srow + (uint32_t)(c0 >> 6) * kCBoxBytes;
+                const int chunk0 = (c0 & 63) >> 3;              // 16-byte chunk inside the 128-byte row
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        if (n0 + c0 + j < N) {                  // N is a multiple of 8 (16-byte rows)
-                            float f[8];
+                for (int j = 0; j < 4; ++j) {
+                    float f[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]) + (bias ? s_bias[c0 + j + i] : 0.f);
-                            uint4 o = make_uint4(pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
-                                                 pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
-                            *reinterpret_cast<uint4 *>(crow + (c0 + j) * 2) = o;
-                        }
-                    }
+                    for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]) + (bias ? s_bias[c0 + 8 * j + i] : 0.f);
+                    const uint32_t dst = box + ((uint32_t)((chunk0 + j) ^ (r & 7)) << 4);     // SWIZZLE_128B
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack2<BF16>(f[0], f[1])),
+                                 "r"(pack2<BF16>(f[2], f[3])), "r"(pack2<BF16>(f[4], f[5])), "r"(pack2<BF16>(f[6], f[7])) : "memory");
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) mbar_arrive(tempty_bar(as));         // TMEM stage drained: the next MMAs may overwrite it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA engine
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+                for (int b = 0; b * 64 < bn; ++b)
+                    tma_store_2d(&map_c, smem_u32(s_c) + (uint32_t)b * kCBoxBytes, n0 + b * 64, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
 
+    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output tiles written
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -270,7 +288,8 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int make_map(CUtensorMap *map, const void *base, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_map(CUtensorMap *map, const void *base, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+             bool store = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is unavailable in this driver");
@@ -282,7 +301,8 @@ int make_map(CUtensorMap *map, const void *base, int dtype, int64_t rows, int64_
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, dtype == SIRGCN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                     const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_128B, store ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d) for a %lld x %lld table, ld %lld", (int)r, (long long)rows,
                   (long long)cols, (long long)ld);
@@ -305,20 +325,22 @@ extern "C" int sirgcn_gemm_tn(const void *a, int64_t lda, const void *b, int64_t
     SIRGCN_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(c) && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 &&
                          lda >= k && ldb >= k && ldc >= n, "operands must have 16-byte aligned rows");
     int bn = n >= kMaxBN ? kMaxBN : (n + 15) / 16 * 16;
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a, map_b, map_c;
     int rc = make_map(&map_a, a, dtype, m, k, lda, kBM);
     if (rc) return rc;
     rc = make_map(&map_b, b, dtype, n, k, ldb, bn);
+    if (rc) return rc;
+    rc = make_map(&map_c, c, dtype, m, n, ldc, kBM, true);
     if (rc) return rc;
     const int tiles = (int)((m + kBM - 1) / kBM) * ((n + bn - 1) / bn);
     const int grid = std::min(tiles, kNumSMs);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == SIRGCN_BF16) {
         SIRGCN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        gemm_tn_kernel<true><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, c, ldc, bias, (int)m, n, k, bn);
+        gemm_tn_kernel<true><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, map_c, bias, (int)m, n, k, bn);
     } else {
         SIRGCN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        gemm_tn_kernel<false><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, c, ldc, bias, (int)m, n, k, bn);
+        gemm_tn_kernel<false><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, map_c, bias, (int)m, n, k, bn);
     }
     SIRGCN_LAUNCHED();
     return SIRGCN_OK;
