@@ -611,7 +611,11 @@ int launch_gs(const sirgcn_edge_args &a, cudaStream_t st) {
         return SIRGCN_EUNSUP;
     }
     auto kern = edge_walk_kernel<T, VPL, MODE, HAS_E, ACT, GS>;
-    SIRGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static std::atomic<int> configured{0};           // per instantiation: raise the opt-in limit only when needed
+    if ((int)smem > configured.load(std::memory_order_relaxed)) {   // (one process drives one GPU)
+        SIRGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.store((int)smem, std::memory_order_relaxed);
+    }
     if (a.n_tiles > 0) {
         kern<<<(unsigned)((a.n_tiles + kWarps - 1) / kWarps), kWarps * 32, smem, st>>>(a, 0);
         SIRGCN_LAUNCHED();

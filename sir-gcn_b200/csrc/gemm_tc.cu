@@ -335,11 +335,15 @@ extern "C" int sirgcn_gemm_tn(const void *a, int64_t lda, const void *b, int64_t
     const int tiles = (int)((m + kBM - 1) / kBM) * ((n + bn - 1) / bn);
     const int grid = std::min(tiles, kNumSMs);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (dtype == SIRGCN_BF16) {
+    static std::atomic<bool> configured{false};
+    if (!configured.load(std::memory_order_relaxed)) {
         SIRGCN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        SIRGCN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        configured.store(true, std::memory_order_relaxed);
+    }
+    if (dtype == SIRGCN_BF16) {
         gemm_tn_kernel<true><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, map_c, bias, (int)m, n, k, bn);
     } else {
-        SIRGCN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         gemm_tn_kernel<false><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, map_c, bias, (int)m, n, k, bn);
     }
     SIRGCN_LAUNCHED();
