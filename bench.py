@@ -32,6 +32,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+# N > 1: compute, barrier, NCCL and 7 copy streams — more hardware queues than the default 8 avoids false ordering
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import torch  # noqa: E402
 from torch import nn  # noqa: E402
@@ -197,9 +199,22 @@ def workload_config(args, w):
             "nodes": n, "edges": e, "d_in": w["d_in"], "d_hidden": w["d"], "layers": w["layers"],
             "agg": w["agg"], "activation": w["act"], "table_dtype": w["dtype"],
             "partition": "single GPU" if args.gpus == 1 else
-            f"1-D destination rows over {args.gpus} GPUs, K all-gather in {args.phases} phase(s); Q and dA all-gathers hidden behind the edge walks",
+            f"1-D destination rows over {args.gpus} GPUs; row tables travel by {transport_name(args)}; layer l+1's K "
+            f"gathered in {args.chunks} destination chunks under layer l's walk, Q and dA gathers under the other walks"
+            + ("" if args.no_input_gather else "; node features of all ranks gathered ahead of the layers (layer 1 projects K/Q locally)"),
             "l2": "inputs >> 126 MB L2, no flush" if e * w["d"] * (4 if w["dtype"] == "f32" else 2) > (1 << 30)
             else "L2 flushed (256 MiB write) between timed steps"}
+
+
+def transport_name(args):
+    kind = os.environ.get("SIRGCN_TRANSPORT", args.transport)
+    if kind == "auto":
+        from sirgcn_b200 import partition
+        kind = partition.AUTO_TRANSPORT
+    return {"peer": "copy-engine pulls from IPC-mapped peer slices",
+            "push": "copy-engine pushes into IPC-mapped peer tables",
+            "pushsm": "a fan-out push kernel writing into IPC-mapped peer tables",
+            "collective": "NCCL all-gathers"}[kind]
 
 
 def scaled_shape(args, w):
@@ -247,13 +262,23 @@ def run_gpu(args, w):
         graph = Graph(src, dst, n, need_eid=False, keep_coo=False)
         del src, dst
         n_local, e_local = n, e
-        run_layer = lambda layer, h: layer(graph, h)
+
+        def run_layers(h):
+            for layer in layers:
+                h = layer(graph, h)
+            return h
     else:
         from sirgcn_b200 import partition
         part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, alpha=2.3, max_deg=w["max_deg"],
-                                                         seed=0, device=dev, phases=args.phases)
+                                                         seed=0, device=dev, transport=args.transport)
         n_local, e_local = part.n_local, part.num_local_edges
-        run_layer = lambda layer, h: partition.partitioned_sirconv(layer, part, h)
+        # the node features of ALL ranks, gathered ahead of the layers (an input: a prefetching loader gathers step
+        # i+1's under step i); layer 1 then projects its K / Q tables locally instead of gathering both in line
+        full_of = {}
+
+        def run_layers(h):
+            return partition.partitioned_sirconv_stack(list(layers), part, h, chunks=args.chunks,
+                                                       feat_full=full_of.get(h.data_ptr()))
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
 
@@ -269,14 +294,14 @@ def run_gpu(args, w):
         hi = min(n_local, lo + chunk)
         gout[lo:hi] = torch.randn((hi - lo, d), generator=gen, device=dev).to(dtype)
     x_dev.requires_grad_(True)
+    if world > 1 and not args.no_input_gather:
+        full_of[x_dev.data_ptr()] = part.all_gather_rows(x_dev.detach())
 
     def step(x):
         x.grad = None
         for p in params:
             p.grad = None
-        h = x
-        for layer in layers:
-            h = run_layer(layer, h)
+        h = run_layers(x)
         check = h.detach().sum(dtype=torch.float32)
         h.backward(gout)
         return check
@@ -332,21 +357,20 @@ def run_gpu(args, w):
     peak_mem = torch.cuda.max_memory_allocated() / 2**30
 
     # per-kernel durations (CUDA events around each C-ABI edge call, inside the timed region)
+    es = torch.empty((), dtype=dtype).element_size()
     per = {}
     for name, t0, t1, rows in timers:
-        acc = per.setdefault(name, [0.0, 0, 0, 0])
+        acc = per.setdefault(name, [0.0, 0, 0])
         acc[0] += t0.elapsed_time(t1)
         acc[1] += 1
-        acc[2], acc[3] = rows.num_pos, rows.n_rows
-    es = torch.empty((), dtype=dtype).element_size()
+        acc[2] += edge_bytes(name, rows.num_pos, rows.n_rows, d * es)
     peak, peak_src = peaks()
     stages = {}
-    for name, (ms, cnt, epos, nrows) in per.items():
-        by = edge_bytes(name, epos, nrows, d * es)
-        avg = ms / cnt
-        stages[name] = {"ms": avg, "bytes": by, "gbs": by / avg / 1e6, "frac": by / avg / 1e6 / peak,
-                        "share_of_step": ms / (ms_step * args.steps)}
-    dom = max(stages, key=lambda k: stages[k]["ms"]) if stages else None
+    for name, (ms, cnt, by_all) in per.items():
+        by, avg = by_all / cnt, ms / cnt            # per C-ABI call (a chunked walk is several calls)
+        stages[name] = {"ms": avg, "bytes": by, "calls_per_step": cnt / args.steps, "gbs": by / avg / 1e6,
+                        "frac": by / avg / 1e6 / peak, "share_of_step": ms / (ms_step * args.steps)}
+    dom = max(stages, key=lambda k: per[k][0]) if stages else None
     traffic = None      # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if dom and world == 1 and os.path.exists(tpath):
@@ -354,8 +378,8 @@ def run_gpu(args, w):
             tj = json.load(f)
         if tj["workload"] == {"nodes": n, "edges": e, "d": d, "dtype": w["dtype"]}:
             traffic = tj.get(dom)
-    tot_ms = sum(s["ms"] for s in stages.values())
-    tot_by = sum(s["bytes"] for s in stages.values())
+    tot_ms = sum(v[0] for v in per.values()) / (args.steps * L)        # per layer: one forward + two backward walks
+    tot_by = sum(v[2] for v in per.values()) / (args.steps * L)
 
     # ---- e2e: node features from pinned host memory, results read back, every step -----------------
     x_dev.grad = None
@@ -367,8 +391,18 @@ def run_gpu(args, w):
     # computes (what a training loop with a prefetching loader does); every step's copy is inside the timed region.
     nbytes_x = x_host.numel() * x_host.element_size()
     headroom = torch.cuda.mem_get_info(dev)[1] - torch.cuda.max_memory_reserved(dev)
-    double = headroom > int(1.25 * nbytes_x) + (2 << 30)
+    # host-resident inputs: gathering them over NVLink every step as well (11.2 GB per rank at 8 GPUs, on the same
+    # NCCL queue as the layers' own table traffic) costs more than it saves — measured 230 vs 185-200 ms per step at
+    # 8 GPUs — so by default the e2e leg lets layer 1 gather its K and Q tables in line instead
+    gather_input = world > 1 and not args.no_input_gather and args.e2e_input_gather
+    if world > 1 and not gather_input:
+        full_of.clear()
+    extra = nbytes_x * (1 + (world if gather_input else 0))     # a second input buffer (+ its gathered copy)
+    double = headroom > int(1.25 * extra) + (2 << 30)
     bufs = [x_dev, torch.empty_like(x_dev).requires_grad_(True)] if double else [x_dev]
+    if gather_input:
+        for b in bufs[1:]:
+            full_of[b.data_ptr()] = torch.empty_like(full_of[x_dev.data_ptr()])
     copy_stream = torch.cuda.Stream(device=dev)
     ready = [torch.cuda.Event() for _ in bufs]        # H2D of buffer b finished
     freed = [torch.cuda.Event() for _ in bufs]        # last step that read buffer b finished
@@ -378,6 +412,8 @@ def run_gpu(args, w):
         with torch.cuda.stream(copy_stream), torch.no_grad():
             copy_stream.wait_event(freed[b])
             bufs[b].copy_(x_host, non_blocking=True)   # this step's inputs: pinned host -> HBM
+            if gather_input:                            # ... and over NVLink to every rank, still on the copy stream
+                part.all_gather_rows(bufs[b].detach(), out=full_of[bufs[b].data_ptr()])
             ready[b].record(copy_stream)
 
     def e2e_step():
@@ -420,8 +456,9 @@ def run_gpu(args, w):
             "config": workload_config(args, w),
             "e2e": {"value": total_edges / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h[0] * world,
-                    "ms_per_step": ms_e2e, "input_pipeline": "double-buffered H2D on a copy stream" if double
-                    else "single buffer, H2D on the compute stream"},
+                    "ms_per_step": ms_e2e, "input_pipeline": ("double-buffered H2D on a copy stream" if double
+                    else "single buffer, H2D on the compute stream") + ("" if world == 1 else
+                    ("; features then gathered over NVLink" if gather_input else "; layer 1 gathers K and Q in line"))},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": None if dom is None else {
@@ -455,7 +492,14 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's nodes/edges (debug)")
     ap.add_argument("--cpu-edges", type=int, default=4_000_000, help="edges of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--phases", type=int, default=1, help="N>1: source chunks of the phased K all-gather / forward walk")
+    ap.add_argument("--chunks", type=int, default=4,
+                    help="N>1: destination chunks of the cross-layer K prefetch (1 = gather each K table whole)")
+    ap.add_argument("--no-input-gather", action="store_true",
+                    help="N>1: do not gather the node features ahead of the layers (layer 1 gathers K and Q in line)")
+    ap.add_argument("--e2e-input-gather", action="store_true",
+                    help="N>1: the e2e leg also gathers every step's node features over NVLink behind their H2D copy")
+    ap.add_argument("--transport", default="auto", choices=["auto", "push", "pushsm", "peer", "collective"],
+                    help="N>1: how row tables travel between ranks (partition.RowPartition.transport)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3

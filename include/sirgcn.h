@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIRGCN_ABI_VERSION 5
+#define SIRGCN_ABI_VERSION 6
 
 /* element types of feature tables (accumulation is always fp32) */
 enum { SIRGCN_F32 = 0, SIRGCN_BF16 = 1, SIRGCN_F16 = 2 };
@@ -221,6 +221,33 @@ int sirgcn_segment_minmax(int32_t n_rows, const int32_t *indptr, const void *m, 
 int sirgcn_segment_minmax_bwd(int64_t num_pos, const int32_t *rsel, const void *dout, int64_t lddo,
                               const int32_t *arg, int64_t ldarg, void *dm, int64_t lddm,
                               int32_t d, int32_t dtype, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Peer-memory transport of the row-partitioned graph (one process per GPU of a node; SURVEY.md §8e — a new
+ * capability, the reference is single-process).  Every rank keeps its slice of a row table (K, Q or the scaled
+ * dA) in a buffer made by sirgcn_peer_alloc; the peers map it with sirgcn_peer_open (CUDA IPC) and the all-gather
+ * of the table is world-1 sirgcn_peer_copy pulls on copy engines over NVLink — no SM is taken from the edge walk
+ * that runs at the same time.  These two are the ONLY entry points that allocate device memory: an IPC-exportable
+ * allocation cannot come from the caller's caching allocator.  sirgcn_peer_alloc zero-fills and may synchronise
+ * the device (setup time only).
+ * sirgcn_peer_barrier orders the ranks on the device: pads[r] (DEVICE array of `world` device pointers) is rank
+ * r's flag pad, uint32[SIRGCN_PEER_MAX_WORLD] inside a peer allocation; the kernel stores `epoch` into slot
+ * `rank` of every peer's pad (release, system scope) and waits until every slot of its own pad has reached
+ * `epoch` (acquire); epochs must grow by one per call on every rank.  If a peer has not arrived after
+ * `timeout_ns` the kernel gives up and sets status[0] = 1 (device int32) instead of hanging. */
+#define SIRGCN_IPC_HANDLE_BYTES 64
+#define SIRGCN_PEER_MAX_WORLD 32
+int sirgcn_peer_alloc(size_t bytes, void **dev_ptr, void *ipc_handle /* [SIRGCN_IPC_HANDLE_BYTES] out */);
+int sirgcn_peer_free(void *dev_ptr);
+int sirgcn_peer_open(const void *ipc_handle, void **dev_ptr);
+int sirgcn_peer_close(void *dev_ptr);
+int sirgcn_peer_copy(void *dst, const void *src, size_t bytes, void *stream);
+/* SM-driven fan-out: every 16-byte vector of src[0..bytes) is read once and written to each of dsts[0..n_dst)
+ * (HOST array of device pointers: peer mappings and/or local buffers) by a kernel of at most n_ctas CTAs —
+ * posted writes over NVLink, for when the copy engines' many-to-many rate is the limit. */
+int sirgcn_peer_push(const void *src, void *const *dsts, int32_t n_dst, size_t bytes, int32_t n_ctas, void *stream);
+int sirgcn_peer_barrier(uint32_t *const *pads, int32_t world, int32_t rank, uint32_t epoch, uint64_t timeout_ns,
+                        int32_t *status, void *stream);
 
 #ifdef __cplusplus
 }

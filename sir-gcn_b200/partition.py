@@ -1,20 +1,23 @@
 """1-D destination-row partition of one large graph over the GPUs of a node (one process per GPU,
-torch.distributed / NCCL over NVLink).  New capability — the reference is single-process — whose
+torch.distributed / NCCL + peer memory over NVLink).  New capability — the reference is single-process — whose
 correctness oracle is "G-rank result == 1-rank result" (SURVEY.md §8e).
 
 Rank r owns node rows [r*n_pad, min(N, (r+1)*n_pad)), n_pad = ceil(N/G): its slice of H, Q, K, A, the
 in-CSR rows of those destinations (column ids stay GLOBAL source ids) and the out-CSC rows of those
-sources (row ids stay GLOBAL destination ids).  Per layer there are three exchanges, two of them hidden:
+sources (row ids stay GLOBAL destination ids).  Per layer three row tables travel (each rank receives the other
+ranks' slices); the schedule keeps the NVLink ports busy while the edge walks run and exposes only the first one:
 
-    forward   K_full  = all_gather(K_loc)                 -> edge_fwd over the local CSR rows   (exposed)
-              Q_full  = all_gather(Q_loc)  issued right behind it on NCCL's stream; it is only needed by the
-                        backward CSC pass, so it travels while the forward edge kernel runs
-    backward  dA_loc *= dst coefficient;  dA_full = all_gather(dA_loc)  travels while
-              dQ_loc  = edge_bwd_q over the local CSR rows (re-uses K_full) runs
-              dK_loc  = edge_bwd_k over the local CSC rows (Q_full, dA_full, K_loc)
-    weights   replicated; dW summed with all_reduce
+    forward   K_1      gathered before the first walk                                         (exposed)
+              K_l+1    produced and gathered in destination chunks WHILE layer l's walk runs: chunk c of
+                       out_l = A_l[c]·W_R^T -> K_l+1[c] = out_l[c]·W_K^T -> pulls of chunk c travel under the walk of c+1
+              Q_L      (last layer) travels behind its own forward walk; it is only needed by the backward CSC pass
+    backward  dA_l    *= dst coefficient, then travels while  dQ_l = edge_bwd_q over the local CSR rows (K_l) runs
+              Q_l-1    travels while  dK_l = edge_bwd_k over the local CSC rows (Q_l, dA_l, local K_l) runs
+    weights   replicated; all layers' dW summed by ONE flat all_reduce at the end of the backward pass
 
-Gathered tables are laid out [G*n_pad, ld], so a global node id indexes them directly.
+Gathered tables are laid out [G*n_pad, ld], so a global node id indexes them directly.  How tables travel is the
+transport: "peer" = copy-engine pulls from IPC-mapped peer slices (peer.py; takes no SM from the walks), or
+"collective" = torch.distributed all-gathers (NCCL kernels; gloo in the CPU tests of this host logic).
 """
 from __future__ import annotations
 
@@ -57,31 +60,130 @@ def build_rows(key, other, n_rows, long_threshold=DEFAULT_LONG_THRESHOLD):
     return CompressedRows(indptr, out, None, long_threshold)
 
 
-def _phase_split(csr: CompressedRows, n_local, n_pad, world, phases, chunk):
-    """(csr_k, [csr_phase_p]): the local in-CSR with source ids remapped to the [P, G, c] layout of the gathered K
-    table, whole and split by source chunk (rows = local destinations in both)."""
-    if phases == 1:
-        return csr, [csr]
-    idx = csr.idx.long()
-    r = idx // n_pad
-    i = idx - r * n_pad
-    p = i // chunk
-    remapped = ((p * world + r) * chunk + (i - p * chunk)).to(torch.int32)
-    csr_k = CompressedRows(csr.indptr, remapped, None, csr.long_threshold)
-    deg = (csr.indptr[1:] - csr.indptr[:-1]).long()
-    dst = torch.repeat_interleave(torch.arange(n_local, dtype=torch.int64, device=idx.device), deg,
-                                  output_size=int(idx.numel()))
-    key = (p * n_local + dst).to(torch.int32)
-    del r, i, dst, deg, idx
-    if key.is_cuda:
-        stacked = build_rows(key, remapped, phases * n_local, csr.long_threshold)
-    else:       # host-side planning (gloo tests): same stable ordering with torch.sort
-        order = torch.sort(key.long(), stable=True)[1]
-        counts = torch.bincount(key.long(), minlength=phases * n_local)
-        indptr = torch.zeros(phases * n_local + 1, dtype=torch.int32)
-        indptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
-        stacked = CompressedRows(indptr, remapped[order].contiguous(), None, csr.long_threshold)
-    return csr_k, [stacked.slice_rows(q * n_local, (q + 1) * n_local) for q in range(phases)]
+class _CollectiveSlice:
+    def __init__(self, local):
+        self.local = local
+
+
+class _Handle:
+    """completion of one (chunk of a) table gather: wait() makes the CURRENT STREAM wait, never the host"""
+
+    def __init__(self, works):
+        self.works = works
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
+class CollectiveTransport:
+    """all-gathers through torch.distributed (NCCL kernels on the GPU, gloo in the CPU tests of the host logic)"""
+    kind = "collective"
+
+    def __init__(self, part):
+        self.part = part
+
+    def acquire(self, rows, ld, dtype, device, zero):
+        return _CollectiveSlice((torch.zeros if zero else torch.empty)((rows, ld), dtype=dtype, device=device))
+
+    def new_full(self, sl, lease):
+        return sl.local.new_empty((self.part.world * sl.local.shape[0], sl.local.shape[1]))
+
+    def gather(self, sl, full, lo=0, hi=None):
+        """rows [lo, hi) of every rank's slice -> full[r*rows + lo : r*rows + hi]; returns a handle"""
+        part, rows = self.part, sl.local.shape[0]
+        hi = rows if hi is None else hi
+        if part.world == 1:
+            full[lo:hi].copy_(sl.local[lo:hi])
+            return _Handle([])
+        if lo == 0 and hi == rows:
+            return _Handle([dist.all_gather_into_tensor(full, sl.local, group=part.group, async_op=True)])
+        views = [full[r * rows + lo:r * rows + hi] for r in range(part.world)]
+        return _Handle([dist.all_gather(views, sl.local[lo:hi], group=part.group, async_op=True)])
+
+    def release(self, sl):
+        pass
+
+
+class PeerTransport:
+    """all-gathers as copy-engine pulls from IPC-mapped peer slices (peer.py): no SM taken from the edge walks"""
+    kind = "peer"
+
+    def __init__(self, part):
+        from . import peer
+        self.pool = peer.PeerPool(part.group)
+
+    def acquire(self, rows, ld, dtype, device, zero):
+        sl = self.pool.acquire(rows, ld, dtype)
+        self.pool.ensure_writable(sl)
+        if zero:
+            sl.local.zero_()
+        return sl
+
+    def new_full(self, sl, lease):
+        return sl.local.new_empty((self.pool.world * sl.rows, sl.ld))
+
+    def gather(self, sl, full, lo=0, hi=None):
+        return self.pool.gather(sl, full, lo, hi)
+
+    def release(self, sl):
+        self.pool.release(sl)
+
+
+class _FullToken:
+    def __init__(self, pf):
+        self.pf = pf
+
+
+class PushTransport:
+    """all-gathers as PUSHES into IPC-mapped gathered tables (peer.py): every rank writes its slice into every
+    peer's table — by copy engines ("push") or by a fan-out kernel of a few CTAs ("pushsm")"""
+
+    def __init__(self, part, mode):
+        from . import peer
+        self.pool = peer.PeerPool(part.group)
+        self.mode = mode
+        self.kind = "push" if mode == "ce" else "pushsm"
+        self._fulls = {}
+
+    def acquire(self, rows, ld, dtype, device, zero):
+        return _CollectiveSlice((torch.zeros if zero else torch.empty)((rows, ld), dtype=dtype, device=device))
+
+    def new_full(self, sl, lease):
+        pf = self.pool.acquire_full(sl.local.shape[0], sl.local.shape[1], sl.local.dtype)
+        self._fulls[pf.local.data_ptr()] = pf
+        lease.add(_FullToken(pf))
+        return pf.local
+
+    def gather(self, sl, full, lo=0, hi=None):
+        return self.pool.push(sl.local, self._fulls[full.data_ptr()], lo, hi, self.mode)
+
+    def release(self, obj):
+        if isinstance(obj, _FullToken):
+            self.pool.release_full(obj.pf)
+
+
+class _Lease:
+    """slices held by one forward call until its backward has run (or its autograd node is dropped)"""
+
+    def __init__(self, transport):
+        self.transport, self.slices = transport, []
+
+    def add(self, sl):
+        self.slices.append(sl)
+        return sl
+
+    def release(self):
+        for sl in self.slices:
+            self.transport.release(sl)
+        self.slices = []
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:       # interpreter shutdown
+            pass
 
 
 class RowPartition:
@@ -91,33 +193,16 @@ class RowPartition:
     in_norm / out_norm / inv_in_deg: fp32 [G*n_pad] GLOBAL coefficient vectors (padding = 1)."""
 
     def __init__(self, num_nodes, rank, world, csr_local, csc_local, in_norm, out_norm, inv_in_deg, group=None,
-                 phases=1):
+                 transport="auto"):
         self.num_nodes_, self.rank, self.world, self.group = int(num_nodes), rank, world, group
+        self._transport, self._transport_kind = None, transport
         self.n_pad = (self.num_nodes_ + world - 1) // world
         self.lo = min(self.num_nodes_, rank * self.n_pad)
         self.hi = min(self.num_nodes_, self.lo + self.n_pad)
         self.csr, self.csc = csr_local, csc_local
         self.in_norm, self.out_norm, self.inv_in_deg = in_norm, out_norm, inv_in_deg
         self.num_local_edges = csr_local.num_pos
-        # Phased forward: every rank's K rows are cut into `phases` chunks of c rows; chunk p of ALL ranks is one
-        # all-gather, and the forward edge pass runs once per chunk over the edges whose source lies in it, so the
-        # walk over chunk p overlaps the transfer of chunks p+1..  The gathered table is laid out [P, G, c, ld]:
-        # global id v = r*n_pad + p*c + j  ->  row (p*G + r)*c + j   (csr_k / csr_phase carry these remapped ids).
-        self.phases = max(1, int(phases)) if world > 1 else 1
-        self.chunk = (self.n_pad + self.phases - 1) // self.phases
-        self.csr_k, self.csr_phase = _phase_split(self.csr, self.n_local, self.n_pad, world, self.phases, self.chunk)
-        if self.phases == 1:
-            self.out_norm_k = out_norm
-        else:       # the per-source coefficient in the layout of the gathered K table
-            P, c, G = self.phases, self.chunk, world
-            v = out_norm.new_ones((G, P * c))
-            v[:, :self.n_pad] = out_norm.view(G, self.n_pad)
-            self.out_norm_k = v.view(G, P, c).transpose(0, 1).contiguous().view(-1)
-
-    @property
-    def k_rows(self):
-        """rows of this rank's padded K buffer (= phases * chunk >= n_pad)"""
-        return self.phases * self.chunk
+        self._row_chunks = {}
 
     @staticmethod
     def bounds(num_nodes, rank, world):
@@ -129,10 +214,27 @@ class RowPartition:
     def n_local(self):
         return self.hi - self.lo
 
+    def row_chunks(self, chunks):
+        """[(lo, hi, CompressedRows or None)]: the local destination rows cut into `chunks` equal ranges of the PADDED
+        slice (the same bounds on every rank, so chunk c of every rank's K slice travels together); the structure
+        covers rows [lo, min(hi, n_local)) and is None when that range is empty."""
+        got = self._row_chunks.get(chunks)
+        if got is None:
+            step = (self.n_pad + chunks - 1) // chunks
+            got = []
+            for c in range(chunks):
+                lo, hi = min(self.n_pad, c * step), min(self.n_pad, (c + 1) * step)
+                top = min(hi, self.n_local)
+                rows = self.csr if (chunks == 1 and top == self.n_local) else \
+                    (self.csr.slice_rows(lo, top) if top > lo else None)
+                got.append((lo, hi, rows))
+            self._row_chunks[chunks] = got
+        return got
+
     # ---- construction ---------------------------------------------------------------------------------
     @classmethod
     def from_csr_csc(cls, csr: CompressedRows, csc: CompressedRows, num_nodes, rank, world, group=None,
-                     in_norm=None, out_norm=None, inv_in_deg=None, phases=1):
+                     in_norm=None, out_norm=None, inv_in_deg=None, transport="auto"):
         """slice replicated whole-graph structures (tests, small graphs)"""
         n = int(num_nodes)
         n_pad, lo, hi = cls.bounds(n, rank, world)
@@ -142,17 +244,17 @@ class RowPartition:
             in_norm, out_norm, inv_in_deg = 1.0 / torch.sqrt(in_deg), 1.0 / torch.sqrt(out_deg), 1.0 / in_deg
         pad = lambda t: torch.cat([t, t.new_ones(world * n_pad - n)]) if world * n_pad > n else t
         return cls(n, rank, world, csr.slice_rows(lo, hi), csc.slice_rows(lo, hi),
-                   pad(in_norm), pad(out_norm), pad(inv_in_deg), group, phases)
+                   pad(in_norm), pad(out_norm), pad(inv_in_deg), group, transport)
 
     @classmethod
-    def from_graph(cls, graph: Graph, rank, world, group=None, phases=1):
+    def from_graph(cls, graph: Graph, rank, world, group=None, transport="auto"):
         """slice an already converted (replicated) Graph; the caller may drop `graph` afterwards"""
         return cls.from_csr_csc(graph.csr, graph.csc, graph.num_nodes(), rank, world, group,
-                                graph.in_norm, graph.out_norm, graph.inv_in_deg, phases)
+                                graph.in_norm, graph.out_norm, graph.inv_in_deg, transport)
 
     @classmethod
     def from_local_edges(cls, num_nodes, rank, world, in_src, in_dst, out_src, out_dst, group=None,
-                         long_threshold=DEFAULT_LONG_THRESHOLD, in_indptr=None, phases=1):
+                         long_threshold=DEFAULT_LONG_THRESHOLD, in_indptr=None, transport="auto"):
         """build from this rank's two edge lists (GLOBAL ids): the edges whose destination is local
         (in_src -> in_dst) and the edges whose source is local (out_src -> out_dst).  When the first list is
         already destination-sorted, pass its local row pointer `in_indptr` instead of `in_dst`.  Degree
@@ -180,11 +282,11 @@ class RowPartition:
                 full.copy_(buf)
             return full
         return cls(n, rank, world, csr, csc, gather(1.0 / torch.sqrt(in_deg)), gather(1.0 / torch.sqrt(out_deg)),
-                   gather(1.0 / in_deg), group, phases)
+                   gather(1.0 / in_deg), group, transport)
 
     @classmethod
     def synthetic_powerlaw(cls, num_nodes, num_edges, rank, world, alpha=2.3, max_deg=None, seed=0, device="cuda",
-                           group=None, long_threshold=DEFAULT_LONG_THRESHOLD, phases=1):
+                           group=None, long_threshold=DEFAULT_LONG_THRESHOLD, transport="auto"):
         """this rank's slice of synth.powerlaw_hashed (the SAME global graph on every world size), generated on
         the device without any edge exchange"""
         from . import synth
@@ -195,7 +297,7 @@ class RowPartition:
         in_indptr = indptr[lo:hi + 1] - indptr[lo]
         del indptr
         return cls.from_local_edges(num_nodes, rank, world, in_src, None, out_src, out_dst, group, long_threshold,
-                                    in_indptr=in_indptr, phases=phases)
+                                    in_indptr=in_indptr, transport=transport)
 
     # ---- coefficients --------------------------------------------------------------------------------------
     def _rows(self, v):
@@ -204,7 +306,7 @@ class RowPartition:
     def scales_rows(self, agg_type):
         """(dst_scale, src_scale) for the CSR walks: dst = local row, src = row of the gathered K table"""
         if agg_type == "sym":
-            return self._rows(self.in_norm), self.out_norm_k
+            return self._rows(self.in_norm), self.out_norm
         if agg_type == "mean":
             return self._rows(self.inv_in_deg), None
         return None, None
@@ -213,36 +315,48 @@ class RowPartition:
         """row (= local source) scale of the CSC walk; its destination scale is folded into dA before the gather"""
         return self._rows(self.out_norm) if agg_type == "sym" else None
 
-    # ---- collectives ------------------------------------------------------------------------------------------
-    def new_rows(self, ld, dtype, device):
-        """[n_pad, ld] buffer whose first n_local rows are this rank's slice of a table"""
-        return torch.empty((self.n_pad, ld), dtype=dtype, device=device)
+    # ---- transport --------------------------------------------------------------------------------------------
+    def transport(self):
+        """how row tables travel between the ranks (CUDA tensors of an NCCL group of one node, except "collective"):
+        "push" / "pushsm" (every rank writes its slice into every peer's IPC-mapped gathered table, by copy engines /
+        by a fan-out kernel), "peer" (copy-engine pulls from IPC-mapped peer slices) or "collective"
+        (torch.distributed all-gathers).  "auto" picks AUTO_TRANSPORT when it applies; the environment variable
+        SIRGCN_TRANSPORT overrides."""
+        if self._transport is None:
+            import os
+            kind = os.environ.get("SIRGCN_TRANSPORT", self._transport_kind)
+            if kind == "auto":
+                on_gpu = self.csr.indptr.is_cuda and self.world > 1 and dist.is_initialized() \
+                    and dist.get_backend(self.group) == "nccl"
+                kind = AUTO_TRANSPORT if on_gpu else "collective"
+            self._transport = {"peer": lambda: PeerTransport(self), "push": lambda: PushTransport(self, "ce"),
+                               "pushsm": lambda: PushTransport(self, "sm"),
+                               "collective": lambda: CollectiveTransport(self)}[kind]()
+        return self._transport
 
-    def all_gather_rows(self, local_pad, async_op=False):
-        """[n_pad, ld] -> ([G*n_pad, ld], work handle or None); rows of rank r land at r*n_pad"""
-        full = local_pad.new_empty((self.world * self.n_pad, local_pad.shape[1]))
+    def all_gather_rows(self, local, out=None):
+        """[n_local, c] rows of this rank -> [G*n_pad, c] with rank r's rows at r*n_pad (padding rows are zero).
+        For INPUT tables such as the node features: gathered once per step ahead of the layers (a prefetching
+        loader does it under the previous step), they let layer 1 project its K and Q tables locally instead of
+        gathering both on the critical path (`feat_full` of partitioned_sirconv_stack)."""
+        full = local.new_empty((self.world * self.n_pad, local.shape[1])) if out is None else out
+        src = local
+        if local.shape[0] != self.n_pad:
+            src = local.new_zeros((self.n_pad, local.shape[1]))
+            src[:local.shape[0]].copy_(local)
         if self.world == 1:
-            full.copy_(local_pad)
-            return full, None
-        work = dist.all_gather_into_tensor(full, local_pad, group=self.group, async_op=async_op)
-        return full, (work if async_op else None)
-
-    def all_gather_k(self, k_pad):
-        """phased gather of K: k_pad [P*c, ld] -> (K_all [P*G*c, ld], [work per chunk]); chunk p of every rank
-        lands in K_all[p*G*c : (p+1)*G*c]"""
-        P, c, G = self.phases, self.chunk, self.world
-        k_all = k_pad.new_empty((P * G * c, k_pad.shape[1]))
-        if G == 1:
-            k_all.copy_(k_pad)
-            return k_all, [None]
-        works = [dist.all_gather_into_tensor(k_all[p * G * c:(p + 1) * G * c], k_pad[p * c:(p + 1) * c],
-                                             group=self.group, async_op=True) for p in range(P)]
-        return k_all, works
+            full.copy_(src)
+        else:
+            dist.all_gather_into_tensor(full, src.contiguous(), group=self.group)
+        return full
 
     def all_reduce_(self, t):
         if self.world > 1 and t is not None:
             dist.all_reduce(t, group=self.group)
         return t
+
+
+AUTO_TRANSPORT = "collective"
 
 
 # bench.py sets this to a list to collect (label, CUDA event) marks on the compute stream (phase breakdown)
@@ -256,125 +370,222 @@ def _mark(label):
         PHASE_MARKS.append((label, ev))
 
 
-def _wait(work):
-    if work is not None:
-        work.wait()        # stream-level wait: the current stream waits for NCCL's, the host does not block
+def _project(x, w, b, dst, n, d, ld):
+    """dst[:n, :d] = x·w^T + b (dst is a [*, ld] slice buffer)"""
+    if n == 0:
+        return
+    if ld == d:
+        gemm.linear_forward(x, w, b, out=dst[:n])
+    else:
+        dst[:n, :d].copy_(gemm.linear_forward(x, w, b))
 
 
-class PartitionedSIRLayerFunction(torch.autograd.Function):
-    """SIRLayerFunction for a row-partitioned graph: same arithmetic per row; K all-gathered in forward, Q and
-    the pre-scaled dA all-gathered behind the edge kernels, weight gradients all-reduced (every rank ends with
-    the full-graph gradient)."""
+def _table(buf, n, d):
+    t = buf[:n, :d]
+    t._sirgcn_padded = True
+    return t
+
+
+class PartitionedSIRStackFunction(torch.autograd.Function):
+    """L stacked SIRConv layers (sum / mean / sym, elementwise σ, no dropout, nothing between the layers) on a
+    row-partitioned graph as ONE autograd node — the unit that can hide the table traffic (module docstring):
+    same arithmetic per row as SIRLayerFunction; every rank ends with the full-graph weight gradients.
+
+    apply(feat, part, cfgs, chunks, backend, feat_full, *weights):  cfgs[l] = (agg_type, act, act_param);
+    weights = (w_q, b_q, w_k, w_r, b_r) per layer, flattened.  feat_full (optional, no gradient): the input rows of
+    ALL ranks (RowPartition.all_gather_rows); the first layer then projects its whole K table (and, in backward, its
+    whole Q table) locally and two of the table transfers disappear."""
 
     @staticmethod
-    def forward(ctx, feat, w_q, b_q, w_k, w_r, b_r, part: RowPartition, agg_type, act, act_param, backend):
-        n, d, dt, dev = part.n_local, w_q.shape[0], feat.dtype, feat.device
-        ld = F_._pad_cols(d, dt)
-        alloc = (torch.zeros if ld != d else torch.empty)
-        _mark("fwd:start")
-        k_pad = alloc((part.k_rows, ld), dtype=dt, device=dev)
-        q_pad = alloc((part.n_pad, ld), dtype=dt, device=dev)
-        wq, wk = w_q.to(dt), w_k.to(dt)
-        if ld == d:
-            gemm.linear_forward(feat, wk, None, out=k_pad[:n])
-        else:
-            k_pad[:n, :d].copy_(gemm.linear_forward(feat, wk, None))
-        k_all, k_works = part.all_gather_k(k_pad)                       # chunk by chunk, in phase order
-        if ld == d:
-            gemm.linear_forward(feat, wq, b_q, out=q_pad[:n])
-        else:
-            q_pad[:n, :d].copy_(gemm.linear_forward(feat, wq, b_q))
-        q_full, wq_h = part.all_gather_rows(q_pad, async_op=True)       # consumed by backward only
-        q, k = q_pad[:n, :d], k_pad[:n, :d]
-        q._sirgcn_padded = k._sirgcn_padded = True
-        kf = k_all[:, :d]
-        kf._sirgcn_padded = True
-        ds, ss = part.scales_rows(agg_type)
-        _mark("fwd:proj")
-        a = F_._alloc_table(n, d, dt, dev, zero=ld != d)
-        for p, work in enumerate(k_works):                              # walk chunk p while chunks p+1.. travel
-            _wait(work)
-            if p == 0:
-                _mark("fwd:wait_K0")
-            backend.forward(part.csr_phase[p], q, kf, None, ds, ss, act, act_param, out=a, accumulate=p > 0)
-        a._sirgcn_padded = True
-        _mark("fwd:edge")
-        out = gemm.linear_forward(a, w_r.to(dt), b_r)
-        _mark("fwd:out")
-        ctx.save_for_backward(feat, q_pad, k_pad, k_all, q_full, a, w_q, w_k, w_r)
-        ctx.q_work = wq_h
-        ctx.part, ctx.agg_type, ctx.act, ctx.act_param, ctx.backend = part, agg_type, act, act_param, backend
-        ctx.has_bias = (b_q is not None, b_r is not None)
-        return out
+    def forward(ctx, feat, part: RowPartition, cfgs, chunks, backend, feat_full, *weights):
+        L = len(cfgs)
+        W = [weights[5 * l:5 * l + 5] for l in range(L)]
+        n, dt, dev = part.n_local, feat.dtype, feat.device
+        tr = part.transport()
+        leases = [_Lease(tr) for _ in range(L)]     # what layer l holds until its backward has run
+        train = any(ctx.needs_input_grad)
+        chunks = max(1, int(chunks)) if part.world > 1 else 1
+        saved, state = [], []
+        h = feat
+        pre = None                          # (k_sl, k_all, [handles]) of the current layer when prefetched
+        for l in range(L):
+            lease = leases[l]
+            w_q, b_q, w_k, w_r, b_r = W[l]
+            agg_type, act, act_param = cfgs[l]
+            d = w_q.shape[0]
+            ld = F_._pad_cols(d, dt)
+            _mark("fwd:start")
+            if l == 0 and feat_full is not None:
+                k_all = torch.empty((feat_full.shape[0], ld), dtype=dt, device=dev) if ld == d else \
+                    torch.zeros((feat_full.shape[0], ld), dtype=dt, device=dev)
+                _project(feat_full.to(dt), w_k.to(dt), None, k_all, feat_full.shape[0], d, ld)
+                k_sl = _CollectiveSlice(k_all[part.rank * part.n_pad:(part.rank + 1) * part.n_pad])
+                k_handles = []
+            elif pre is None:
+                k_sl = lease.add(tr.acquire(part.n_pad, ld, dt, dev, zero=ld != d))
+                _project(h, w_k.to(dt), None, k_sl.local, n, d, ld)
+                k_all = tr.new_full(k_sl, lease)
+                k_handles = [tr.gather(k_sl, k_all)]
+            else:
+                k_sl, k_all, k_handles = pre
+                pre = None
+            q_sl = lease.add(tr.acquire(part.n_pad, ld, dt, dev, zero=ld != d))
+            _project(h, w_q.to(dt), b_q, q_sl.local, n, d, ld)
+            # Q of the remote destinations is consumed by the backward CSC pass only.  The last layer's travels behind
+            # its own forward walk; an earlier layer's is left for the backward pass (the ports carry K_l+1 now).
+            q_full = q_h = None
+            if train and l == L - 1:
+                q_full = tr.new_full(q_sl, lease)
+                q_h = tr.gather(q_sl, q_full)
+            q, kf = _table(q_sl.local, n, d), _table(k_all, k_all.shape[0], d)
+            ds, ss = part.scales_rows(agg_type)
+            _mark("fwd:proj")
+            a = F_._alloc_table(n, d, dt, dev, zero=ld != d)
+            for hnd in k_handles:
+                hnd.wait()
+            _mark("fwd:wait_K")
+            if l + 1 < L:
+                # walk in destination chunks; chunk c of the NEXT layer's K is produced and sent while c+1 is walked
+                w_kn = W[l + 1][2].to(dt)
+                dn = w_kn.shape[0]
+                ldn = F_._pad_cols(dn, dt)
+                kn_sl = leases[l + 1].add(tr.acquire(part.n_pad, ldn, dt, dev, zero=ldn != dn))
+                kn_all = tr.new_full(kn_sl, leases[l + 1])
+                out = torch.empty((n, w_r.shape[0]), dtype=dt, device=dev)
+                kn_handles = []
+                for lo, hi, rows in part.row_chunks(chunks):
+                    if rows is not None:
+                        top = lo + rows.n_rows
+                        backend.forward(rows, q[lo:top], kf, None, None if ds is None else ds[lo:top], ss, act,
+                                        act_param, out=a[lo:top])
+                        gemm.linear_forward(a[lo:top], w_r.to(dt), b_r, out=out[lo:top])
+                        if ldn == dn:
+                            gemm.linear_forward(out[lo:top], w_kn, None, out=kn_sl.local[lo:top])
+                        else:
+                            kn_sl.local[lo:top, :dn].copy_(gemm.linear_forward(out[lo:top], w_kn, None))
+                    if hi > lo:
+                        kn_handles.append(tr.gather(kn_sl, kn_all, lo, hi))
+                pre = (kn_sl, kn_all, kn_handles)
+                a._sirgcn_padded = True
+                _mark("fwd:edge")
+            else:
+                backend.forward(part.csr, q, kf, None, ds, ss, act, act_param, out=a)
+                a._sirgcn_padded = True
+                _mark("fwd:edge")
+                out = gemm.linear_forward(a, w_r.to(dt), b_r)
+            _mark("fwd:out")
+            saved += [h, k_all, a]
+            state.append(dict(k_sl=k_sl, q_sl=q_sl, q_full=q_full, q_h=q_h, d=d, ld=ld))
+            h = out
+        if not train:
+            for lease in leases:
+                lease.release()
+            return h
+        ctx.save_for_backward(*saved, *weights, feat_full)
+        ctx.leases, ctx.state, ctx.part, ctx.cfgs, ctx.backend, ctx.L = leases, state, part, cfgs, backend, L
+        return h
 
     @staticmethod
     def backward(ctx, gout):
-        feat, q_pad, k_pad, k_all, q_full, a, w_q, w_k, w_r = ctx.saved_tensors
-        part, be = ctx.part, ctx.backend
-        n, d, dt, dev = part.n_local, w_q.shape[0], q_pad.dtype, q_pad.device
-        ld = q_pad.shape[1]
+        L, part, be, leases, state = ctx.L, ctx.part, ctx.backend, ctx.leases, ctx.state
+        tensors = ctx.saved_tensors
+        saved, weights, feat_full = tensors[:3 * L], tensors[3 * L:-1], tensors[-1]
+        tr = part.transport()
+        n = part.n_local
         need = ctx.needs_input_grad
-        gout = gout.to(dt)
-        gout = gout if gout.stride(-1) == 1 else gout.contiguous()
-        _mark("bwd:start")
-        adt = torch.float64 if dt == torch.float64 else torch.float32      # dtype of the reduced weight gradients
-        dw_r = (gout.t() @ a).to(adt) if need[4] else None
-        db_r = gemm.column_sum(gout, adt) if (need[5] and ctx.has_bias[1]) else None
-        # dA, scaled by the destination coefficient BEFORE it travels: the CSC pass then needs no scale lookup
-        alloc = (torch.zeros if ld != d else torch.empty)
-        da_pad = alloc((part.n_pad, ld), dtype=dt, device=dev)
-        da = da_pad[:n, :d]
-        if ld == d:
-            gemm.linear_dgrad(gout, w_r.to(dt), out=da)
-        else:
-            da.copy_(gemm.linear_dgrad(gout, w_r.to(dt)))
-        ds, ss = part.scales_rows(ctx.agg_type)
-        if ds is not None:
-            da.mul_(ds[:n].to(dt).unsqueeze(1))
-        da._sirgcn_padded = True
-        da_full, wa_h = part.all_gather_rows(da_pad, async_op=True)      # travels while dQ is computed
-        q, k = q_pad[:n, :d], k_pad[:n, :d]
-        q._sirgcn_padded = k._sirgcn_padded = True
-        kf, qf, daf = k_all[:, :d], q_full[:, :d], da_full[:, :d]
-        kf._sirgcn_padded = qf._sirgcn_padded = daf._sirgcn_padded = True
-        dq = F_._alloc_table(n, d, dt, dev, zero=ld != d)
-        dk = F_._alloc_table(n, d, dt, dev, zero=ld != d)
-        _mark("bwd:dA")
-        be.backward_q(part.csr_k, q, kf, None, da, None, ss, ctx.act, ctx.act_param, False, out=dq)
-        _mark("bwd:edge_q")
-        _wait(ctx.q_work)
-        _wait(wa_h)
-        _mark("bwd:wait_Q_dA")
-        be.backward_k(part.csc, qf, k, None, daf, None, part.scale_cols_rows(ctx.agg_type), ctx.act, ctx.act_param,
-                      out=dk)
-        _mark("bwd:edge_k")
-        featd = feat.to(dt)
-        # weight gradients: fp32 partials of every rank in ONE flat all-reduce
-        parts = [(dq.t() @ featd).to(adt) if need[1] else None,
-                 gemm.column_sum(dq, adt) if (need[2] and ctx.has_bias[0]) else None,
-                 (dk.t() @ featd).to(adt) if need[3] else None, dw_r, db_r]
-        live = [t for t in parts if t is not None]
+        wneed = [need[6 + 5 * l:11 + 5 * l] for l in range(L)]
+        grads = [[None] * 5 for _ in range(L)]       # fp32 partials of this rank, reduced at the end
+        g = gout
+        for l in reversed(range(L)):
+            feat, k_all, a = saved[3 * l:3 * l + 3]
+            w_q, b_q, w_k, w_r, b_r = weights[5 * l:5 * l + 5]
+            agg_type, act, act_param = ctx.cfgs[l]
+            st, lease = state[l], leases[l]
+            d, ld, q_sl, k_sl = st["d"], st["ld"], st["q_sl"], st["k_sl"]
+            dt, dev = q_sl.local.dtype, q_sl.local.device
+            adt = torch.float64 if dt == torch.float64 else torch.float32
+            g = g.to(dt)
+            g = g if g.stride(-1) == 1 else g.contiguous()
+            _mark("bwd:start")
+            # dA, scaled by the destination coefficient BEFORE it travels: the CSC pass then needs no scale lookup
+            da_sl = lease.add(tr.acquire(part.n_pad, ld, dt, dev, zero=ld != d))
+            da = _table(da_sl.local, n, d)
+            if n:
+                if ld == d:
+                    gemm.linear_dgrad(g, w_r.to(dt), out=da)
+                else:
+                    da.copy_(gemm.linear_dgrad(g, w_r.to(dt)))
+            ds, ss = part.scales_rows(agg_type)
+            if ds is not None:
+                da.mul_(ds[:n].to(dt).unsqueeze(1))
+            da_full = tr.new_full(da_sl, lease)
+            da_h = tr.gather(da_sl, da_full)                              # travels while dQ is computed
+            if wneed[l][3]:
+                grads[l][3] = (g.t() @ a).to(adt)
+            if wneed[l][4] and b_r is not None:
+                grads[l][4] = gemm.column_sum(g, adt)
+            q, k = _table(q_sl.local, n, d), _table(k_sl.local, n, d)
+            kf, daf = _table(k_all, k_all.shape[0], d), _table(da_full, da_full.shape[0], d)
+            # dQ and dK are the two halves of ONE [n, 2·ld] buffer: the projection's weight and input gradients are
+            # then single GEMMs over the concatenated [W_Q; W_K]
+            dqk = (torch.empty if ld == d else torch.zeros)((n, 2 * ld), dtype=dt, device=dev)
+            dq, dk = _table(dqk, n, d), dqk[:, ld:ld + d]
+            dk._sirgcn_padded = True
+            _mark("bwd:dA")
+            be.backward_q(part.csr, q, kf, None, da, None, ss, act, act_param, False, out=dq)
+            _mark("bwd:edge_q")
+            if l == 0 and feat_full is not None and st["q_h"] is None:
+                # the first layer's Q table of ALL destinations is a projection of the gathered input: made here
+                qf_buf = (torch.empty if ld == d else torch.zeros)((feat_full.shape[0], ld), dtype=dt, device=dev)
+                _project(feat_full.to(dt), w_q.to(dt), b_q, qf_buf, feat_full.shape[0], d, ld)
+                st["q_full"] = qf_buf
+            else:
+                if st["q_h"] is None:       # not prefetched by the layer above (cannot happen for l = L-1)
+                    st["q_full"] = tr.new_full(q_sl, lease)
+                    st["q_h"] = tr.gather(q_sl, st["q_full"])
+                st["q_h"].wait()
+            da_h.wait()
+            _mark("bwd:wait_Q_dA")
+            if l > 1 or (l == 1 and feat_full is None):
+                # the layer below needs its Q table next: it travels under this CSC walk
+                sb = state[l - 1]
+                sb["q_full"] = tr.new_full(sb["q_sl"], leases[l - 1])
+                sb["q_h"] = tr.gather(sb["q_sl"], sb["q_full"])
+            qf = _table(st["q_full"], st["q_full"].shape[0], d)
+            be.backward_k(part.csc, qf, k, None, daf, None, part.scale_cols_rows(agg_type), act, act_param, out=dk)
+            _mark("bwd:edge_k")
+            lease.release()
+            st["q_full"] = None
+            del da_full, daf, qf, kf, k_all
+            featd = feat.to(dt)
+            if wneed[l][0] or wneed[l][2]:
+                dw_qk = (dqk.t() @ featd).to(adt)                          # [2·ld, d_in]
+                grads[l][0], grads[l][2] = dw_qk[:d], dw_qk[ld:ld + d]
+            if wneed[l][1] and b_q is not None:
+                grads[l][1] = gemm.column_sum(dqk, adt)[:d]
+            g = None
+            if l > 0 or need[0]:
+                w_cat = (torch.zeros if ld != d else torch.empty)((2 * ld, w_q.shape[1]), dtype=dt, device=dev)
+                w_cat[:d].copy_(w_q)
+                w_cat[ld:ld + d].copy_(w_k)
+                g = gemm.linear_dgrad(dqk, w_cat)
+            _mark("bwd:grads")
+        # weight gradients of all layers: fp32 partials of every rank in ONE flat all-reduce
+        live = [(l, i, t) for l in range(L) for i, t in enumerate(grads[l]) if t is not None and wneed[l][i]]
+        out_w = [None] * (5 * L)
         if live:
-            flat = torch.cat([t.reshape(-1) for t in live])
+            flat = torch.cat([t.reshape(-1) for _, _, t in live])
             part.all_reduce_(flat)
             off = 0
-            for t in live:
-                t.copy_(flat[off:off + t.numel()].view_as(t))
+            for l, i, t in live:
+                out_w[5 * l + i] = flat[off:off + t.numel()].view(t.shape).to(weights[5 * l + i].dtype)
                 off += t.numel()
-        dw_q, db_q, dw_k, dw_r, db_r = [None if t is None else t.to(w.dtype)
-                                        for t, w in zip(parts, (w_q, w_q, w_k, w_r, w_r))]
-        dfeat = None
-        if need[0]:
-            dfeat = gemm.linear_dgrad(dq, w_q.to(dt))
-            dfeat.add_(gemm.linear_dgrad(dk, w_k.to(dt)))
-            dfeat = dfeat.to(feat.dtype)
-        _mark("bwd:grads")
-        return dfeat, dw_q, db_q, dw_k, dw_r, db_r, None, None, None, None, None
+        _mark("bwd:allreduce")
+        dfeat = g.to(saved[0].dtype) if need[0] else None
+        return (dfeat, None, None, None, None, None, *out_w)
 
 
-def partitioned_sirconv(layer, part: RowPartition, feat_loc, backend=CudaEdgeBackend):
-    """Run a `SIRConv` (sum / mean / sym, elementwise σ, no dropout) on this rank's rows of a
-    partitioned graph.  `feat_loc` = rows [part.lo, part.hi) of the node features."""
+def _layer_args(layer):
     from .conv import _SUM_LIKE, classify_activation
     known = classify_activation(layer.activation)
     if layer._agg_type not in _SUM_LIKE or known is None or not layer._plain():
@@ -382,8 +593,30 @@ def partitioned_sirconv(layer, part: RowPartition, feat_loc, backend=CudaEdgeBac
                                   "(sum/mean/sym with ReLU/LeakyReLU/GELU/Identity)")
     if layer.training and layer.dropout.p > 0:
         raise NotImplementedError("dropout inside the partitioned layer is not supported")
+    lq, lk, lr = layer.linear_query, layer.linear_key, layer.linear_relation
+    return (layer._agg_type, known[0], known[1]), (lq.weight, lq.bias, lk.weight, lr.weight, lr.bias)
+
+
+def partitioned_sirconv_stack(layers, part: RowPartition, feat_loc, chunks=4, backend=CudaEdgeBackend,
+                              feat_full=None):
+    """Run consecutive `SIRConv` layers (output of one = input of the next, nothing in between) on this rank's rows
+    of a partitioned graph as one autograd node; `chunks` = destination chunks of the cross-layer K prefetch.
+    `feat_loc` = rows [part.lo, part.hi) of the node features; `feat_full` (optional) = the rows of all ranks,
+    part.all_gather_rows(feat_loc) — an input gathered ahead of time instead of two projections gathered in line."""
     if feat_loc.shape[0] != part.n_local:
         raise ValueError(f"feat_loc has {feat_loc.shape[0]} rows, this rank owns {part.n_local}")
-    lq, lk, lr = layer.linear_query, layer.linear_key, layer.linear_relation
-    return PartitionedSIRLayerFunction.apply(feat_loc, lq.weight, lq.bias, lk.weight, lr.weight, lr.bias, part,
-                                             layer._agg_type, known[0], known[1], backend)
+    if feat_full is not None and feat_full.shape[0] != part.world * part.n_pad:
+        raise ValueError(f"feat_full has {feat_full.shape[0]} rows, expected {part.world * part.n_pad}")
+    if feat_full is not None and feat_full.requires_grad:
+        feat_full = feat_full.detach()
+    cfgs, weights = [], []
+    for layer in layers:
+        c, w = _layer_args(layer)
+        cfgs.append(c)
+        weights += list(w)
+    return PartitionedSIRStackFunction.apply(feat_loc, part, tuple(cfgs), chunks, backend, feat_full, *weights)
+
+
+def partitioned_sirconv(layer, part: RowPartition, feat_loc, backend=CudaEdgeBackend):
+    """Run one `SIRConv` (sum / mean / sym, elementwise σ, no dropout) on this rank's rows of a partitioned graph."""
+    return partitioned_sirconv_stack([layer], part, feat_loc, 1, backend)

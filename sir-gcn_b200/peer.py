@@ -1,0 +1,339 @@
+"""Peer-memory transport of the row-partitioned graph (partition.py): all-gathers of the K / Q / dA row tables as
+copy-engine pulls over NVLink instead of NCCL kernels (include/sirgcn.h, "Peer-memory transport").
+
+Why: at 8 GPUs the three all-gathers of a layer move as many bytes over NVLink as the edge walks move through HBM
+in the same time, so they must overlap the walks without slowing them.  An NCCL all-gather occupies SMs and
+issues its loads/stores from them; a copy-engine pull takes no SM at all.
+
+    slice = pool.acquire(rows, ld, dtype)      # this rank's [rows, ld] slice, IPC-mapped by every peer
+    pool.ensure_writable(slice)
+    ...producer kernels write slice.local (all of it, or rows lo..hi)...
+    h = pool.gather(slice, full[, lo, hi])     # barrier ("rows written everywhere") + world-1 pulls on copy streams
+    ...independent work...
+    h.wait()                                   # the current stream waits for the pulls
+    pool.release(slice)                        # may be handed out again
+
+Hazards.  Every rank runs the same sequence of acquire / gather / wait / release (SPMD).  A slice may be overwritten
+once every peer has finished pulling from it; a peer finishes its pulls before the `wait` it enqueues on its compute
+stream, and a barrier starts only when the issuing compute stream has reached it — so ANY barrier issued after that
+`wait` proves it, once the local compute stream has waited for that barrier (directly, or through the pulls of a later
+gather, which run behind their barrier).  The pool numbers the barriers: a slice remembers the newest barrier issued
+at its last `wait`, `joined` is the newest barrier the compute stream has waited for, and `ensure_writable` enqueues an
+extra blocking barrier only when joined <= that number.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+_BARRIER_TIMEOUT_NS = 20_000_000_000      # a peer that has not arrived after 20 s is reported, nothing hangs
+
+
+class _RawDeviceBuffer:
+    """exposes a raw device allocation through __cuda_array_interface__ so torch can view it"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerSlice:
+    """this rank's slice of a gathered row table: `local` [rows, ld] lives in an IPC-exported allocation,
+    `peer_ptr[r]` is rank r's slice mapped into this process (None for the own rank)"""
+
+    def __init__(self, rows, ld, dtype, base, local, peer_ptr):
+        self.rows, self.ld, self.dtype = rows, ld, dtype
+        self.base, self.local, self.peer_ptr = base, local, peer_ptr
+        self.row_bytes = ld * local.element_size()
+        self.waited_at = -1         # index of the newest barrier issued when the last pull of this slice was waited for
+        self.pending = []           # PullHandles of gathers that have not been waited for yet
+
+
+class PullHandle:
+    def __init__(self, pool, sl, events, barrier_index):
+        self.pool, self.slice, self.events, self.barrier_index = pool, sl, events, barrier_index
+
+    def wait(self):
+        """the current stream waits for the pulls (the host does not block)"""
+        if self.events is None:
+            return
+        cur = torch.cuda.current_stream(self.pool.device)
+        for ev in self.events:
+            cur.wait_event(ev)
+        self.events = None
+        pool, sl = self.pool, self.slice
+        pool.joined = max(pool.joined, self.barrier_index)     # the pulls ran behind that barrier
+        sl.waited_at = pool.barriers
+        sl.pending = [h for h in sl.pending if h is not self]
+
+
+class PeerFull:
+    """a gathered table [world*rows, ld] in an IPC-exported allocation: every peer PUSHES its slice into its row range
+    (`peer_ptr[r]` = rank r's table mapped into this process)"""
+
+    def __init__(self, rows, ld, dtype, base, local, peer_ptr):
+        self.rows, self.ld, self.dtype = rows, ld, dtype
+        self.base, self.local, self.peer_ptr = base, local, peer_ptr
+        self.row_bytes = ld * local.element_size()
+        self.released_at = 0        # newest barrier issued when the last reader of this table was enqueued
+
+
+class PushHandle:
+    def __init__(self, pool, done, barrier_index):
+        self.pool, self.done, self.barrier_index = pool, done, barrier_index
+
+    def wait(self):
+        """the current stream waits until every rank's rows have landed in the local table"""
+        if self.done is not None:
+            torch.cuda.current_stream(self.pool.device).wait_event(self.done)
+            self.done = None
+        self.pool.joined = max(self.pool.joined, self.barrier_index)
+
+
+class PeerPool:
+    """IPC-mapped row-table slices of one process group (one process per GPU of one node) + the pull all-gather"""
+
+    def __init__(self, group=None, device=None, barrier="flags"):
+        if not dist.is_initialized():
+            raise RuntimeError("PeerPool needs an initialised torch.distributed process group")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.world > 32:
+            raise ValueError("PeerPool covers the GPUs of one node (world <= 32)")
+        self.lib = _lib.lib()
+        self.free, self.all = {}, []
+        self.barriers = 0           # barriers issued so far (the same count on every rank: SPMD)
+        self.joined = 0             # newest barrier whose completion the compute stream has waited for
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, self.world - 1))]
+        # every barrier runs on ONE stream of its own, so that barriers execute in issue order on every rank and a
+        # gather's barrier does not make the compute stream wait for the slowest peer
+        self.sync_stream = torch.cuda.Stream(device=self.device)
+        self.push_stream = torch.cuda.Stream(device=self.device, priority=-1)   # SM-driven pushes: scheduled first
+        self.push_ctas = int(os.environ.get("SIRGCN_PUSH_CTAS", "32"))
+        self.free_full, self.all_full = {}, []
+        self._last_done = (0, None)     # (index, done event) of the newest barrier
+        self.barrier_kind = os.environ.get("SIRGCN_PEER_BARRIER", barrier)
+        self._nccl_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # flag pads: one uint32 per peer, in a peer allocation of their own
+        self._pad_base, pad_peers = self._alloc_mapped(4096)
+        pads = [self._pad_base if r == self.rank else pad_peers[r] for r in range(self.world)]
+        self._pads = torch.tensor(pads, dtype=torch.int64, device=self.device)
+        self._pad_peers = pad_peers
+        self._epoch = 0
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)      # every pad is mapped (and zero) before the first flag is written
+
+    # ---- allocation ---------------------------------------------------------------------------------------------
+    def _alloc_mapped(self, nbytes):
+        """collective: (own device pointer, [peer r's allocation mapped here or None])"""
+        handle = (C.c_ubyte * 64)()
+        base = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sirgcn_peer_alloc(C.c_size_t(nbytes), C.byref(base), handle), "sirgcn_peer_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        peers = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                peers.append(None)
+                continue
+            p = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(h)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.sirgcn_peer_open(buf, C.byref(p)), "sirgcn_peer_open")
+            peers.append(p.value)
+        return base.value, peers
+
+    def acquire(self, rows, ld, dtype) -> PeerSlice:
+        """collective the first time a (rows, ld, dtype) slice is needed; afterwards slices are recycled"""
+        key = (rows, ld, dtype)
+        lst = self.free.setdefault(key, [])
+        if lst:
+            return lst.pop()
+        es = torch.empty((), dtype=dtype).element_size()
+        nbytes = max(16, rows * ld * es)
+        base, peers = self._alloc_mapped(nbytes)
+        raw = torch.as_tensor(_RawDeviceBuffer(base, nbytes), device=self.device)
+        local = raw.view(dtype)[:rows * ld].view(rows, ld)
+        sl = PeerSlice(rows, ld, dtype, base, local, peers)
+        self.all.append(sl)
+        return sl
+
+    def release(self, sl: PeerSlice):
+        for h in list(sl.pending):          # never waited for (e.g. backward never ran): drain first
+            h.wait()
+        self.free.setdefault((sl.rows, sl.ld, sl.dtype), []).append(sl)
+
+    # ---- ordering -----------------------------------------------------------------------------------------------
+    def barrier(self, blocking=True, after=()):
+        """device-side barrier of all ranks: it starts once the current stream has reached this point (and the events
+        in `after` have fired) and runs on the pool's sync stream; with `blocking` the current stream also waits for
+        it.  Returns (index, done event)."""
+        self.barriers += 1
+        index = self.barriers
+        cur = torch.cuda.current_stream(self.device)
+        if self.world == 1:
+            self.joined = index
+            return index, None
+        here = torch.cuda.Event()
+        here.record(cur)
+        self.sync_stream.wait_event(here)
+        for ev in after:
+            self.sync_stream.wait_event(ev)
+        if self.barrier_kind == "nccl":
+            with torch.cuda.stream(self.sync_stream):
+                dist.all_reduce(self._nccl_flag, group=self.group)
+        else:
+            self._epoch += 1
+            with torch.cuda.device(self.device):
+                rc = self.lib.sirgcn_peer_barrier(C.c_void_p(self._pads.data_ptr()), C.c_int32(self.world),
+                                                  C.c_int32(self.rank), C.c_uint32(self._epoch & 0xffffffff),
+                                                  C.c_uint64(_BARRIER_TIMEOUT_NS), C.c_void_p(self._status.data_ptr()),
+                                                  C.c_void_p(self.sync_stream.cuda_stream))
+            _lib.check(rc, "sirgcn_peer_barrier")
+        done = torch.cuda.Event()
+        done.record(self.sync_stream)
+        self._last_done = (index, done)
+        if blocking:
+            cur.wait_event(done)
+            self.joined = index
+        return index, done
+
+    def check(self):
+        """host-side: raise if any barrier gave up waiting for a peer (synchronises the device)"""
+        if int(self._status.item()) != 0:
+            raise RuntimeError("sirgcn_peer_barrier timed out: a peer rank never arrived")
+
+    def ensure_writable(self, sl: PeerSlice):
+        """call before the producer overwrites sl.local: fences the peers' pulls of its previous contents"""
+        for h in list(sl.pending):
+            h.wait()
+        if sl.waited_at >= 0 and self.joined <= sl.waited_at:
+            self.barrier(blocking=True)
+        sl.waited_at = -1
+
+    # ---- the all-gather -----------------------------------------------------------------------------------------
+    def gather(self, sl: PeerSlice, full, lo=0, hi=None):
+        """rows [lo, hi) of every rank's slice -> full[r*rows + lo : r*rows + hi] (full is [world*rows, ld]).  The pulls
+        run on the pool's copy streams behind a barrier ("every rank has written these rows") that does not block
+        the current stream; the own rows are copied on the current stream.  Returns a PullHandle."""
+        hi = sl.rows if hi is None else hi
+        if self.world == 1:
+            full[lo:hi].copy_(sl.local[lo:hi])
+            return PullHandle(self, sl, None, self.barriers)
+        index, done = self.barrier(blocking=False)
+        events = []
+        nbytes, off = (hi - lo) * sl.row_bytes, lo * sl.row_bytes
+        for i in range(1, self.world):
+            peer = (self.rank + i) % self.world             # staggered: at any moment the ranks read different peers
+            st = self.streams[i - 1]
+            st.wait_event(done)
+            dst = full.data_ptr() + peer * sl.rows * sl.row_bytes + off
+            with torch.cuda.device(self.device):
+                rc = self.lib.sirgcn_peer_copy(C.c_void_p(dst), C.c_void_p(sl.peer_ptr[peer] + off), C.c_size_t(nbytes),
+                                               C.c_void_p(st.cuda_stream))
+            _lib.check(rc, "sirgcn_peer_copy")
+            ev = torch.cuda.Event()
+            ev.record(st)
+            events.append(ev)
+        full[self.rank * sl.rows + lo:self.rank * sl.rows + hi].copy_(sl.local[lo:hi])
+        h = PullHandle(self, sl, events, index)
+        sl.pending.append(h)
+        return h
+
+    # ---- push variant: the gathered tables are the peer-mapped objects ------------------------------------------
+    def acquire_full(self, rows, ld, dtype) -> PeerFull:
+        """collective the first time a [world*rows, ld] table of this shape is needed; recycled afterwards"""
+        key = (rows, ld, dtype)
+        lst = self.free_full.setdefault(key, [])
+        if lst:
+            return lst.pop()
+        es = torch.empty((), dtype=dtype).element_size()
+        nbytes = max(16, self.world * rows * ld * es)
+        base, peers = self._alloc_mapped(nbytes)
+        raw = torch.as_tensor(_RawDeviceBuffer(base, nbytes), device=self.device)
+        local = raw.view(dtype)[:self.world * rows * ld].view(self.world * rows, ld)
+        pf = PeerFull(rows, ld, dtype, base, local, peers)
+        self.all_full.append(pf)
+        return pf
+
+    def release_full(self, pf: PeerFull):
+        """call after the last kernel that reads pf.local has been enqueued on the current stream"""
+        pf.released_at = self.barriers
+        self.free_full.setdefault((pf.rows, pf.ld, pf.dtype), []).append(pf)
+
+    def push(self, src, pf: PeerFull, lo=0, hi=None, mode="ce"):
+        """rows [lo, hi) of this rank's slice `src` ([rows, ld], any local tensor that stays alive until the handle has
+        been waited for) -> rows rank*rows + lo.. of EVERY rank's table.  mode "ce": one copy-engine write per peer;
+        "sm": one fan-out kernel of a few CTAs (sirgcn_peer_push).  Two barriers frame the transfer, neither blocks
+        the current stream: "every rank is done reading the table's previous contents" (skipped when a barrier has
+        been issued since the table was released) and "every rank's rows have landed".  Returns a PushHandle."""
+        hi = pf.rows if hi is None else hi
+        cur = torch.cuda.current_stream(self.device)
+        mine = self.rank * pf.rows
+        if self.world == 1:
+            pf.local[lo:hi].copy_(src[lo:hi])
+            return PushHandle(self, None, self.barriers)
+        if self.barriers > pf.released_at and self._last_done[0] > pf.released_at:
+            free_ev = self._last_done[1]
+        else:
+            _, free_ev = self.barrier(blocking=False)
+        ready = torch.cuda.Event()
+        ready.record(cur)                                   # the producer of src[lo:hi]
+        nbytes, off = (hi - lo) * pf.row_bytes, (mine + lo) * pf.row_bytes
+        src_ptr = src.data_ptr() + lo * src.stride(0) * src.element_size()
+        assert src.stride(0) == pf.ld and src.stride(1) == 1
+        events = []
+        if mode == "sm":
+            st = self.push_stream
+            st.wait_event(free_ev)
+            st.wait_event(ready)
+            targets = [pf.peer_ptr[(self.rank + i) % self.world] + off for i in range(1, self.world)]
+            targets.append(pf.base + off)
+            arr = (C.c_void_p * len(targets))(*targets)
+            with torch.cuda.device(self.device):
+                rc = self.lib.sirgcn_peer_push(C.c_void_p(src_ptr), arr, C.c_int32(len(targets)), C.c_size_t(nbytes),
+                                               C.c_int32(self.push_ctas), C.c_void_p(st.cuda_stream))
+            _lib.check(rc, "sirgcn_peer_push")
+            ev = torch.cuda.Event()
+            ev.record(st)
+            events.append(ev)
+        else:
+            for i in range(1, self.world):
+                peer = (self.rank + i) % self.world
+                st = self.streams[i - 1]
+                st.wait_event(free_ev)
+                st.wait_event(ready)
+                with torch.cuda.device(self.device):
+                    rc = self.lib.sirgcn_peer_copy(C.c_void_p(pf.peer_ptr[peer] + off), C.c_void_p(src_ptr),
+                                                   C.c_size_t(nbytes), C.c_void_p(st.cuda_stream))
+                _lib.check(rc, "sirgcn_peer_copy")
+                ev = torch.cuda.Event()
+                ev.record(st)
+                events.append(ev)
+            pf.local[mine + lo:mine + hi].copy_(src[lo:hi])
+        index, done = self.barrier(blocking=False, after=events)
+        return PushHandle(self, done, index)
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        for sl in self.all + self.all_full:
+            for p in sl.peer_ptr:
+                if p:
+                    self.lib.sirgcn_peer_close(C.c_void_p(p))
+        for p in self._pad_peers:
+            if p:
+                self.lib.sirgcn_peer_close(C.c_void_p(p))
+        if self.world > 1:
+            dist.barrier(group=self.group)      # nobody frees memory a peer still has mapped
+        for sl in self.all + self.all_full:
+            sl.local = None
+            self.lib.sirgcn_peer_free(C.c_void_p(sl.base))
+        self.lib.sirgcn_peer_free(C.c_void_p(self._pad_base))
+        self.all, self.free, self.all_full, self.free_full = [], {}, [], {}

@@ -97,46 +97,68 @@ def _case(seed, n, e, d_in, d, d_out, act, agg, dtype=torch.float64):
 
 
 def _reference(src, dst, n, layer, x, gout):
+    """layer: one RefSIRConv or a list of them applied back to back"""
+    layers = layer if isinstance(layer, (list, tuple)) else [layer]
     xr = x.clone().requires_grad_(True)
-    out = layer(RefGraph(src, dst, n), xr)
-    grads = torch.autograd.grad(out, [xr] + list(layer.parameters()), gout)
+    g = RefGraph(src, dst, n)
+    out = xr
+    for l in layers:
+        out = l(g, out)
+    grads = torch.autograd.grad(out, [xr] + [p for l in layers for p in l.parameters()], gout)
     return out.detach(), grads
 
 
-def _gloo_worker(rank, world, port, agg, act, phases, ret):
+def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         n = 37                              # not divisible by the world size: padding rows exist
-        src, dst, ref, x, gout = _case(3, n, 400, 6, 12, 5, act, agg)
-        out_ref, g_ref = _reference(src, dst, n, ref, x, gout)
+        src, dst, ref, x, gout = _case(3, n, 400, 6, 12, 6, act, agg)
+        torch.manual_seed(11)
+        refs = [ref] + [RefSIRConv(6, 12, 6, ACTS[act](), agg_type=agg).double() for _ in range(n_layers - 1)]
+        out_ref, g_ref = _reference(src, dst, n, refs, x, gout)
         c = csr_csc_ref(src, dst, n)
         csr = CompressedRows(c[0], c[1], None)
         csc = CompressedRows(c[3], c[4], None)
-        part = partition.RowPartition.from_csr_csc(csr, csc, n, rank, world, phases=phases)
-        assert len(part.csr_phase) == phases and sum(c.num_pos for c in part.csr_phase) == part.csr.num_pos
-        layer = SIRConv(6, 12, 5, ACTS[act](), agg_type=agg).double()
-        layer.load_state_dict(ref.state_dict())
+        part = partition.RowPartition.from_csr_csc(csr, csc, n, rank, world)
+        assert part.transport().kind == "collective"
+        cuts = part.row_chunks(chunks)
+        assert len(cuts) == chunks and cuts[0][0] == 0 and cuts[-1][1] == part.n_pad
+        assert sum(r.num_pos for _, _, r in cuts if r is not None) == part.csr.num_pos
+        layers = []
+        for r in refs:
+            layer = SIRConv(6, 12, 6, ACTS[act](), agg_type=agg).double()
+            layer.load_state_dict(r.state_dict())
+            layers.append(layer)
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
-        out = partition.partitioned_sirconv(layer, part, xl, backend=TorchEdgeBackend)
-        grads = torch.autograd.grad(out, [xl] + list(layer.parameters()), gout[part.lo:part.hi])
+        x_full = part.all_gather_rows(xl.detach()) if use_full else None
+        if use_full:
+            assert x_full.shape[0] == world * part.n_pad and torch.equal(x_full[:n], x)
+        out = partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks, backend=TorchEdgeBackend,
+                                                  feat_full=x_full)
+        grads = torch.autograd.grad(out, [xl] + [p for l in layers for p in l.parameters()], gout[part.lo:part.hi])
         # degree coefficients are fp32 by design (the kernels read fp32 scales): 1e-6; pure sums: 1e-10
         tol = dict(rtol=1e-10, atol=1e-12) if agg == "sum" else dict(rtol=1e-6, atol=1e-7)
         ok = torch.allclose(out, out_ref[part.lo:part.hi], **tol)
         ok &= torch.allclose(grads[0], g_ref[0][part.lo:part.hi], **tol)
         for a, b in zip(grads[1:], g_ref[1:]):          # every rank holds the FULL-graph weight gradient
             ok &= torch.allclose(a, b, **tol)
+        with torch.no_grad():
+            ok &= torch.allclose(partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks,
+                                                                     backend=TorchEdgeBackend, feat_full=x_full), out)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("agg,act,phases", [("sum", "relu", 1), ("mean", "leaky", 2), ("sym", "gelu", 3)])
-def test_partition_gloo_world2_matches_single_process(agg, act, phases):
+@pytest.mark.parametrize("agg,act,n_layers,chunks,use_full", [
+    ("sum", "relu", 1, 1, False), ("mean", "leaky", 2, 3, False), ("sym", "gelu", 3, 2, False),
+    ("sym", "leaky", 1, 1, True), ("mean", "relu", 2, 4, True)])
+def test_partition_gloo_world2_matches_single_process(agg, act, n_layers, chunks, use_full):
     world, port = 2, _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_gloo_worker, args=(world, port, agg, act, phases, ret), nprocs=world, join=True)
+        mp.spawn(_gloo_worker, args=(world, port, agg, act, n_layers, chunks, use_full, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
 
 
@@ -199,43 +221,71 @@ def test_partition_from_hashed_generator_matches_whole_graph_slices():
         assert torch.equal(csc.indptr, whole.csc.indptr) and torch.equal(csc.idx, whole.csc.idx)
 
 
-def _nccl_worker(rank, world, port, ret):
+def _nccl_worker(rank, world, port, transport, chunks, barrier, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["SIRGCN_TRANSPORT"], os.environ["SIRGCN_PEER_BARRIER"] = transport, barrier
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from sirgcn_b200 import synth
         n, e, d = 20011, 600000, 128
-        part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, seed=3, device=dev, long_threshold=64,
-                                                         phases=2)
+        part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, seed=3, device=dev, long_threshold=64)
+        assert part.transport().kind == transport
         # same device as the partition: the degree law is drawn with the device's RNG
         src, dst, _ = synth.powerlaw_hashed(n, e, seed=3, device=dev, index_dtype=torch.int64)
         src, dst = src.cpu(), dst.cpu()
         torch.manual_seed(0)
         # a smooth σ: with ReLU/LeakyReLU the fp32-vs-fp64 comparison at this size (77 M pre-activations) is dominated
         # by σ' flipping for the handful of |z| < 1e-7 elements, not by arithmetic error
-        ref = RefSIRConv(d, d, d, nn.GELU(), agg_type="mean")
+        refs = [RefSIRConv(d, d, d, nn.GELU(), agg_type="mean") for _ in range(2)]
         x, gout = torch.randn(n, d), torch.randn(n, d)
-        out_ref, g_ref = _reference(src, dst, n, ref.double(), x.double(), gout.double())
-        layer = SIRConv(d, d, d, nn.GELU(), agg_type="mean").to(dev)
-        layer.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+        layers = []
+        for r in refs:
+            layer = SIRConv(d, d, d, nn.GELU(), agg_type="mean").to(dev)
+            layer.load_state_dict({k: v.float() for k, v in r.state_dict().items()})
+            layers.append(layer)
+        out_ref, g_ref = _reference(src, dst, n, [r.double() for r in refs], x.double(), gout.double())
+        params = [p for l in layers for p in l.parameters()]
         xl = x[part.lo:part.hi].to(dev).requires_grad_(True)
-        out = partition.partitioned_sirconv(layer, part, xl)
-        grads = torch.autograd.grad(out, [xl] + list(layer.parameters()), gout[part.lo:part.hi].to(dev))
+        for it in range(3):     # repeated steps recycle the peer slices (overwrite fences) and must stay bit-identical
+            out = partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks)
+            grads = torch.autograd.grad(out, [xl] + params, gout[part.lo:part.hi].to(dev))
+            if it == 0:
+                first = [out.clone()] + [g.clone() for g in grads]
+            else:
+                assert all(torch.equal(a, b) for a, b in zip(first, [out] + list(grads))), "step not repeatable"
+        with torch.no_grad():   # inference: nothing is held for a backward that never comes
+            assert torch.equal(partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks), first[0])
+        # the input gathered ahead of time (layer 1 projects its K / Q tables locally): same result
+        x_full = part.all_gather_rows(xl.detach())
+        out_f = partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks, feat_full=x_full)
+        grads_f = torch.autograd.grad(out_f, [xl] + params, gout[part.lo:part.hi].to(dev))
+        assert all(_rel(a, b) < 1e-6 for a, b in zip([out_f] + list(grads_f), first))
+        # layer by layer (no cross-layer prefetch, whole-table projections) agrees with the stack (the library SGEMM
+        # may pick another kernel for a row chunk, so not bit for bit in fp32)
+        h = xl
+        for layer in layers:
+            h = partition.partitioned_sirconv(layer, part, h)
+        assert _rel(h, first[0]) < 1e-6
+        if transport == "peer":
+            part.transport().pool.check()
         errs = [_rel(out, out_ref[part.lo:part.hi]), _rel(grads[0], g_ref[0][part.lo:part.hi])]
         errs += [_rel(a, b) for a, b in zip(grads[1:], g_ref[1:])]
-        ret[rank] = [float(f"{x:.3e}") for x in errs]      # out, dfeat, dW_Q, db_Q, dW_K, dW_R, db_R
+        ret[rank] = [float(f"{x:.3e}") for x in errs]      # out, dfeat, then (dW_Q, db_Q, dW_K, dW_R, db_R) per layer
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-def test_partition_nccl_world2():
+@pytest.mark.parametrize("transport,chunks,barrier", [("collective", 3, "flags"), ("peer", 4, "flags"),
+                                                      ("peer", 1, "nccl"), ("push", 4, "flags"),
+                                                      ("pushsm", 3, "flags")])
+def test_partition_nccl_world2(transport, chunks, barrier):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     world, port = 2, _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_nccl_worker, args=(world, port, ret), nprocs=world, join=True)
+        mp.spawn(_nccl_worker, args=(world, port, transport, chunks, barrier, ret), nprocs=world, join=True)
         assert len(ret) == 2 and max(max(v) for v in ret.values()) < 1e-5, dict(ret)
