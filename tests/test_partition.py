@@ -289,3 +289,62 @@ def test_partition_nccl_world2(transport, chunks, barrier):
         ret = mgr.dict()
         mp.spawn(_nccl_worker, args=(world, port, transport, chunks, barrier, ret), nprocs=world, join=True)
         assert len(ret) == 2 and max(max(v) for v in ret.values()) < 1e-5, dict(ret)
+
+
+# ---- batched small graphs: plain data parallelism -------------------------------------
+def _ddp_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        from sirgcn_b200 import Graph, SIREConv, synth
+
+        def model():
+            torch.manual_seed(0)
+            return nn.ModuleList([SIREConv(5 if i == 0 else 64, 1, 64, 64, nn.LeakyReLU(0.2), agg_type="sum")
+                                  for i in range(2)]).to(dev)
+
+        def batch(seed):
+            src, dst, n, pos, dist_e = synth.cifar_like(num_graphs=16, seed=seed)
+            g = torch.Generator().manual_seed(seed)
+            x = torch.cat([torch.rand(n, 3, generator=g), pos], 1)
+            return Graph(src.to(dev), dst.to(dev), n), x.to(dev), dist_e.unsqueeze(1).to(dev)
+
+        def loss_of(m, b):
+            g, h, ef = b
+            for conv in m:
+                h = conv(g, h, ef)
+            return h.square().mean()
+
+        class Wrap(nn.Module):          # DDP wants one module whose forward returns the loss inputs
+            def __init__(self, convs):
+                super().__init__()
+                self.convs = convs
+
+            def forward(self, b):
+                return loss_of(self.convs, b)
+
+        ddp = DDP(Wrap(model()), device_ids=[rank])
+        ddp(batch(100 + rank)).backward()                       # this rank's own 16-graph batch
+        got = [p.grad.clone() for p in ddp.parameters()]
+        ref = Wrap(model())                                     # one process, both batches, averaged
+        sum(loss_of(ref.convs, batch(100 + r)) for r in range(world)).div(world).backward()
+        errs = [_rel(a, p.grad) for a, p in zip(got, ref.parameters())]
+        ret[rank] = max(errs)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_data_parallel_batches_world2():
+    """config C run data-parallel: per-rank batches of kNN graphs, replicated weights, DDP's gradient all-reduce —
+    the layers are ordinary autograd Functions, so DistributedDataParallel applies unchanged"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_ddp_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert len(ret) == 2 and max(ret.values()) < 1e-5, dict(ret)
