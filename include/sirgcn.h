@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIRGCN_ABI_VERSION 6
+#define SIRGCN_ABI_VERSION 7
 
 /* element types of feature tables (accumulation is always fp32) */
 enum { SIRGCN_F32 = 0, SIRGCN_BF16 = 1, SIRGCN_F16 = 2 };
@@ -95,6 +95,25 @@ size_t sirgcn_rows_build_workspace_bytes(int64_t num_pos, int32_t num_rows);
 int sirgcn_rows_build(const int32_t *key, const int32_t *other, int64_t num_pos, int32_t num_rows,
                       int32_t *indptr, int32_t *other_sorted, int32_t *eid_sorted,
                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* Edge-subset view of a converted graph, WITHOUT sorting: replaces the per-layer, per-step graph rebuild behind
+ * DropEdge (models/utils.py:96-102, used by zinc/model.py:50, super-pixel/model.py:44, sbm-dataset/model.py:42,
+ * wiki-cs/model.py:41), where DGL's remove_edges makes a new graph whose formats are converted again.
+ * keep[e] != 0 marks the edges of the parent (by edge id) that stay.  Kept edges are renumbered in edge-id order:
+ * new_id[e] = number of kept edges with id < e (new_id has num_edges + 1 entries, new_id[num_edges] = number kept;
+ * the caller reads it to size the views).  Because the parent's orderings are stable, compaction of its in-CSR and
+ * out-CSC gives exactly the structures sirgcn_csr_build would produce from the kept COO edges (bit-exact, tested).
+ * sub_* arrays are sized for num_edges entries (the first new_id[num_edges] are written); sub_eid_* may be NULL.
+ * The parent must carry edge ids (eid_in / eid_out). */
+size_t sirgcn_edge_subgraph_workspace_bytes(int64_t num_edges);
+int sirgcn_edge_subgraph(const uint8_t *keep, int64_t num_edges, int32_t num_nodes,
+                         const int32_t *indptr_in, const int32_t *col_src, const int32_t *eid_in,
+                         const int32_t *indptr_out, const int32_t *row_dst, const int32_t *eid_out,
+                         int32_t *new_id /* [num_edges + 1] */,
+                         int32_t *sub_indptr_in, int32_t *sub_col_src, int32_t *sub_eid_in,
+                         int32_t *sub_indptr_out, int32_t *sub_row_dst, int32_t *sub_eid_out,
+                         float *in_norm, float *out_norm, float *inv_in_deg,
+                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* Schedule only (graph already in CSR form, e.g. generated on device): fills one
  * sirgcn_schedule and counts[0..1] = {n_long, n_chunks}. */

@@ -19,6 +19,7 @@ DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 EXPORTS = (
     "sirgcn_last_error", "sirgcn_abi_version", "sirgcn_launch_count",
     "sirgcn_csr_build_workspace_bytes", "sirgcn_csr_build", "sirgcn_schedule_build",
+    "sirgcn_edge_subgraph_workspace_bytes", "sirgcn_edge_subgraph",
     "sirgcn_num_tiles", "sirgcn_tiles_build", "sirgcn_rows_build_workspace_bytes", "sirgcn_rows_build",
     "sirgcn_edge_partial_bytes", "sirgcn_edge_fwd", "sirgcn_edge_bwd_q", "sirgcn_edge_bwd_k",
     "sirgcn_gemm_tn", "sirgcn_colsum_workspace_bytes", "sirgcn_colsum", "sirgcn_gather_add", "sirgcn_segment_sum", "sirgcn_segment_minmax", "sirgcn_segment_minmax_bwd",
@@ -66,6 +67,8 @@ def lib():
         l.sirgcn_launch_count.restype = C.c_uint64
         l.sirgcn_csr_build_workspace_bytes.restype = C.c_size_t
         l.sirgcn_csr_build_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+        l.sirgcn_edge_subgraph_workspace_bytes.restype = C.c_size_t
+        l.sirgcn_edge_subgraph_workspace_bytes.argtypes = [C.c_int64]
         l.sirgcn_rows_build_workspace_bytes.restype = C.c_size_t
         l.sirgcn_rows_build_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
         l.sirgcn_colsum_workspace_bytes.restype = C.c_size_t

@@ -4,6 +4,7 @@
 // The stable LSD radix sort is cub::DeviceRadixSort (ships with the CUDA toolkit); everything
 // else is hand-written.  Bit-exact against oracle/csr_ref.c and torch.sort(stable=True).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 
@@ -106,6 +107,33 @@ __global__ void tiles_kernel(const int32_t *__restrict__ indptr, int32_t num_row
     }
 }
 
+// ---- edge-subset view of a converted graph (no sort: compaction keeps the parent's stable order) ---------------
+__global__ void keep_flags_kernel(const uint8_t *__restrict__ keep, const int32_t *__restrict__ eid,
+                                  int32_t *__restrict__ flag, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        flag[i] = keep[eid ? eid[i] : i] ? 1 : 0;
+}
+
+// positions: prefix[p] = number of kept positions before p (exclusive scan of the flags, prefix[n] = total)
+__global__ void compact_rows_kernel(const uint8_t *__restrict__ keep, const int32_t *__restrict__ eid,
+                                    const int32_t *__restrict__ other, const int32_t *__restrict__ prefix,
+                                    const int32_t *__restrict__ new_id, int32_t *__restrict__ other_out,
+                                    int32_t *__restrict__ eid_out, int64_t n) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t e = eid[p];
+        if (!keep[e]) continue;
+        const int32_t q = prefix[p];
+        other_out[q] = other[p];
+        if (eid_out) eid_out[q] = new_id[e];
+    }
+}
+
+__global__ void compact_indptr_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ prefix,
+                                      int32_t num_rows, int32_t *__restrict__ indptr_out) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= num_rows; r += gridDim.x * blockDim.x)
+        indptr_out[r] = prefix[indptr[r]];
+}
+
 struct SortScratch {
     int32_t *keys[2];
     int32_t *vals[2];
@@ -192,6 +220,71 @@ int sirgcn_tiles_build(const int32_t *indptr, int32_t num_rows, int64_t num_edge
     tiles_kernel<<<std::min(blocks_for((int64_t)num_rows + 1), (unsigned)kNumSMs * 16), kThreads, 0, st>>>(
         indptr, num_rows, n_tiles, tile_row);
     SIRGCN_LAUNCHED();
+    return SIRGCN_OK;
+}
+
+size_t sirgcn_edge_subgraph_workspace_bytes(int64_t num_edges) {
+    using namespace sirgcn;
+    size_t scan = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan, (int32_t *)nullptr, (int32_t *)nullptr, num_edges + 1);
+    // flags [E+1] + prefix [E+1] + cub scratch
+    return 2 * align_up((size_t)(num_edges + 1) * sizeof(int32_t)) + align_up(scan) + 256;
+}
+
+int sirgcn_edge_subgraph(const uint8_t *keep, int64_t num_edges, int32_t num_nodes,
+                         const int32_t *indptr_in, const int32_t *col_src, const int32_t *eid_in,
+                         const int32_t *indptr_out, const int32_t *row_dst, const int32_t *eid_out,
+                         int32_t *new_id, int32_t *sub_indptr_in, int32_t *sub_col_src, int32_t *sub_eid_in,
+                         int32_t *sub_indptr_out, int32_t *sub_row_dst, int32_t *sub_eid_out,
+                         float *in_norm, float *out_norm, float *inv_in_deg,
+                         void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace sirgcn;
+    SIRGCN_CHECK_ARG(num_edges >= 0 && num_edges < (1LL << 31) && num_nodes >= 0, "bad num_edges/num_nodes");
+    SIRGCN_CHECK_ARG(indptr_in && indptr_out && sub_indptr_in && sub_indptr_out && new_id, "indptr/new_id arrays missing");
+    SIRGCN_CHECK_ARG(num_edges == 0 || (keep && col_src && eid_in && row_dst && eid_out && sub_col_src && sub_row_dst),
+                     "edge arrays missing (the parent graph must carry edge ids)");
+    SIRGCN_CHECK_ARG(workspace && workspace_bytes >= sirgcn_edge_subgraph_workspace_bytes(num_edges), "workspace too small");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t E = num_edges;
+    char *base = reinterpret_cast<char *>(workspace);
+    int32_t *flag = reinterpret_cast<int32_t *>(base);
+    int32_t *prefix = reinterpret_cast<int32_t *>(base + align_up((size_t)(E + 1) * sizeof(int32_t)));
+    void *cub_tmp = base + 2 * align_up((size_t)(E + 1) * sizeof(int32_t));
+    size_t scan = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan, flag, prefix, E + 1);
+    const unsigned grid = std::max(1u, std::min(blocks_for(E + 1), (unsigned)kNumSMs * 16));
+    const unsigned grid_n = std::max(1u, std::min(blocks_for(num_nodes + 1), (unsigned)kNumSMs * 16));
+    SIRGCN_CUDA(cudaMemsetAsync(flag, 0, (size_t)(E + 1) * sizeof(int32_t), st));
+    // 1. new edge ids: rank of every kept edge among the kept ones (edge-id order is preserved)
+    if (E) {
+        keep_flags_kernel<<<grid, kThreads, 0, st>>>(keep, nullptr, flag, E);
+        SIRGCN_LAUNCHED();
+    }
+    SIRGCN_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, scan, flag, prefix, E + 1, st));
+    g_launches.fetch_add(1);
+    SIRGCN_CUDA(cudaMemcpyAsync(new_id, prefix, (size_t)(E + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    // 2./3. both compressed-row structures: flags in stored order -> exclusive scan -> compaction
+    const int32_t *ips[2] = {indptr_in, indptr_out}, *others[2] = {col_src, row_dst}, *eids[2] = {eid_in, eid_out};
+    int32_t *sips[2] = {sub_indptr_in, sub_indptr_out}, *sothers[2] = {sub_col_src, sub_row_dst},
+            *seids[2] = {sub_eid_in, sub_eid_out};
+    for (int s = 0; s < 2; ++s) {
+        if (E) {
+            keep_flags_kernel<<<grid, kThreads, 0, st>>>(keep, eids[s], flag, E);
+            SIRGCN_LAUNCHED();
+        }
+        SIRGCN_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, scan, flag, prefix, E + 1, st));
+        g_launches.fetch_add(1);
+        if (E) {
+            compact_rows_kernel<<<grid, kThreads, 0, st>>>(keep, eids[s], others[s], prefix, new_id, sothers[s], seids[s], E);
+            SIRGCN_LAUNCHED();
+        }
+        compact_indptr_kernel<<<grid_n, kThreads, 0, st>>>(ips[s], prefix, num_nodes, sips[s]);
+        SIRGCN_LAUNCHED();
+    }
+    if ((in_norm || out_norm || inv_in_deg) && num_nodes > 0) {
+        norms_kernel<<<grid_n, kThreads, 0, st>>>(sub_indptr_in, sub_indptr_out, num_nodes, in_norm, out_norm, inv_in_deg);
+        SIRGCN_LAUNCHED();
+    }
     return SIRGCN_OK;
 }
 

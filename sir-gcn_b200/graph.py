@@ -148,6 +148,63 @@ class Graph:
         self.src, self.dst = (src, dst) if keep_coo else (None, None)
         self._lazy = {}
 
+    # --- edge-subset views: the DropEdge fast path (models/utils.py:96-102) ---------------------
+    def edge_subgraph(self, keep):
+        """(sub, new_id): the graph restricted to the edges with keep[e] != 0, converted WITHOUT sorting
+        (sirgcn_edge_subgraph: compaction of this graph's stable CSR / CSC).  Kept edges are renumbered in edge-id
+        order — exactly what DGL's remove_edges does — so per-edge features of the sub-graph are `efeat[keep]`;
+        new_id[e] is the new id of kept edge e.  Bit-identical to Graph(src[keep], dst[keep], N)."""
+        if self.csr.eid is None:
+            raise RuntimeError("edge_subgraph needs a graph built with need_eid=True")
+        E, N, dev = self.num_edges_, self.num_nodes_, self.device
+        keep = keep.to(device=dev)
+        if keep.numel() != E:
+            raise ValueError(f"keep has {keep.numel()} entries, the graph has {E} edges")
+        keep8 = (keep != 0).to(torch.uint8).contiguous()
+        i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
+        f32 = lambda n: torch.empty(n, dtype=torch.float32, device=dev)
+        new_id = i32(E + 1)
+        ip_in, idx_in, eid_in, ip_out, idx_out, eid_out = i32(N + 1), i32(E), i32(E), i32(N + 1), i32(E), i32(E)
+        sub = object.__new__(Graph)
+        sub.in_norm, sub.out_norm, sub.inv_in_deg = f32(N), f32(N), f32(N)
+        L = _lib.lib()
+        nbytes = L.sirgcn_edge_subgraph_workspace_bytes(C.c_int64(E))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        c, o = self.csr, self.csc
+        with torch.cuda.device(dev):
+            rc = L.sirgcn_edge_subgraph(
+                _lib.ptr(keep8), C.c_int64(E), C.c_int32(N),
+                _lib.ptr(c.indptr), _lib.ptr(c.idx), _lib.ptr(c.eid), _lib.ptr(o.indptr), _lib.ptr(o.idx), _lib.ptr(o.eid),
+                _lib.ptr(new_id), _lib.ptr(ip_in), _lib.ptr(idx_in), _lib.ptr(eid_in),
+                _lib.ptr(ip_out), _lib.ptr(idx_out), _lib.ptr(eid_out),
+                _lib.ptr(sub.in_norm), _lib.ptr(sub.out_norm), _lib.ptr(sub.inv_in_deg),
+                _lib.ptr(ws), C.c_size_t(nbytes), _lib.stream_ptr(dev))
+        _lib.check(rc, "sirgcn_edge_subgraph")
+        kept = int(new_id[E])               # the one host sync: how many edges stay
+        del ws
+        thr = c.long_threshold
+        sub.num_nodes_, sub.num_edges_, sub.device = N, kept, dev
+        sub.csr = CompressedRows(ip_in, idx_in[:kept], eid_in[:kept], thr)
+        sub.csc = CompressedRows(ip_out, idx_out[:kept], eid_out[:kept], thr)
+        if self.src is not None:
+            sel = keep8.bool()
+            sub.src, sub.dst = self.src[sel], self.dst[sel]
+        else:
+            sub.src = sub.dst = None
+        sub._lazy = {}
+        return sub, new_id[:E]
+
+    def drop_edges(self, p, generator=None):
+        """DropEdge(p) on the converted graph (dgl.transforms.DropEdge semantics: every edge is removed
+        independently with probability p): returns (sub-graph, keep mask) — index per-edge features with the mask.
+        p = 0 returns this graph itself: nothing to convert."""
+        E, dev = self.num_edges_, self.device
+        if p <= 0 or E == 0:
+            return self, torch.ones(E, dtype=torch.bool, device=dev)
+        keep = torch.rand(E, device=dev, generator=generator) >= p
+        sub, _ = self.edge_subgraph(keep)
+        return sub, keep
+
     # --- the slice of the DGLGraph API the layer relies on (conv.py:50-55) ---------------------
     def num_nodes(self):
         return self.num_nodes_

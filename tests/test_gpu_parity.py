@@ -200,6 +200,44 @@ def test_edge_stage_bitwise_repeatable_and_threshold_independent_shape():
     assert rel_err(out2, runs[0][0]) < FP32_RTOL
 
 
+# ---- edge-subset views (DropEdge fast path): bit-exact against a fresh conversion -------------------
+@pytest.mark.parametrize("n,e,p,seed", [(1, 0, 0.5, 0), (7, 40, 0.3, 1), (300, 5000, 0.1, 2), (300, 5000, 1.0, 3),
+                                        (20000, 300000, 0.5, 4), (50, 4000, 0.0, 5)])
+def test_edge_subgraph_bit_exact(n, e, p, seed):
+    src, dst = rand_graph(n, e, seed, hub=0 if e else None)
+    g = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
+    gen = torch.Generator().manual_seed(seed)
+    keep = torch.rand(e, generator=gen) >= p
+    sub, new_id = g.edge_subgraph(keep.to(DEV))
+    ref = Graph(src[keep].to(DEV), dst[keep].to(DEV), n, long_threshold=64)
+    assert sub.num_edges() == int(keep.sum()) == ref.num_edges()
+    for a, b in ((sub.csr, ref.csr), (sub.csc, ref.csc)):
+        assert torch.equal(a.indptr, b.indptr) and torch.equal(a.idx, b.idx) and torch.equal(a.eid, b.eid)
+        assert (a.n_long, a.n_chunks, a.n_tiles) == (b.n_long, b.n_chunks, b.n_tiles)
+    for a, b in ((sub.in_norm, ref.in_norm), (sub.out_norm, ref.out_norm), (sub.inv_in_deg, ref.inv_in_deg)):
+        assert torch.equal(a, b)
+    assert torch.equal(new_id.cpu()[keep].long(), torch.arange(int(keep.sum())))      # renumbered in edge-id order
+    if e:
+        assert torch.equal(sub.src.cpu().long(), src[keep]) and torch.equal(sub.dst.cpu().long(), dst[keep])
+
+
+def test_drop_edges_layer_matches_oracle_on_kept_edges():
+    """SIREConv on the DropEdge view == the oracle on the kept COO edges with efeat[keep] (zinc/model.py:50)"""
+    n, e = 200, 3000
+    src, dst = rand_graph(n, e, 21, hub=5)
+    g = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
+    assert g.drop_edges(0.0)[0] is g
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    sub, keep = g.drop_edges(0.25, generator=gen)
+    assert 0 < sub.num_edges() < e
+    keep_c = keep.cpu()
+    ref, gpu = make_pair(RefSIREConv, SIREConv, 16, 5, 64, 32, nn.LeakyReLU(0.2), agg_type="sym")
+    x, ef = torch.randn(n, 16), torch.randn(e, 5)
+    out_r = ref.double()(RefGraph(src[keep_c], dst[keep_c], n), x.double(), ef[keep_c].double())
+    out_g = gpu(sub, x.to(DEV), ef.to(DEV)[keep])
+    assert rel_err(out_g, out_r) < FP32_RTOL
+
+
 # ---- whole layers --------------------------------------------------------------------------------
 def make_pair(cls_ref, cls_gpu, *args, **kw):
     torch.manual_seed(0)
