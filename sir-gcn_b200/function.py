@@ -206,6 +206,7 @@ class SIRLayerFunction(torch.autograd.Function):
         ctx.save_for_backward(feat, qk, e, a, w_qk, w_r, b_qk if recompute_qk else None)
         ctx.graph, ctx.agg_type, ctx.act, ctx.act_param, ctx.d = graph, agg_type, act, act_param, d
         ctx.has_bias = (b_qk is not None, b_r is not None)
+        ctx.lean = bool(recompute_qk)      # the re-made [Q|K] belongs to backward alone: it may be overwritten
         return out
 
     @staticmethod
@@ -227,16 +228,32 @@ class SIRLayerFunction(torch.autograd.Function):
         da = gemm.linear_dgrad(gout, w_r.to(qk.dtype), pad_to=_pad_cols(d, qk.dtype))[:, :d]   # [N, d]
         da._sirgcn_padded = True
         ds, ss = g.scales(ctx.agg_type)
-        dqk = (torch.empty if ldp == d else torch.zeros)(qk.shape, dtype=qk.dtype, device=qk.device)
-        dq, dk = dqk[:, :d], dqk[:, ldp:ldp + d]
-        # the dQ pass leaves dA scaled by the destination coefficient (in place: `da` is ours)
-        _, de = edge_backward_q(g.csr, q, k, e, da, ds, ss, ctx.act, ctx.act_param, need[3], out=dq,
-                                scale_da_inplace=True)
-        edge_backward_k(g.csc, q, k, e, da, None, ss, ctx.act, ctx.act_param, out=dk)
-        del da
+        if ctx.lean:
+            # memory-lean order for tables of many GB (the 50 M-node graph): dQ goes to a buffer of its own, dK is
+            # written IN PLACE over K (the CSC walk reads K[v] only as the own operand of row v, before it stores
+            # dK[v]; long rows store in the finalize kernel, after every chunk has read K[v]), then dQ is copied over
+            # Q — the [Q|K] buffer has become [dQ|dK] and no second [N, 2·ld] buffer ever existed: 12.8 GB less at
+            # the peak for one extra 12.8 GB copy (≈ 4 ms of a 400 ms layer)
+            dq_buf = _alloc_table(q.shape[0], d, qk.dtype, qk.device, zero=ldp != d)
+            _, de = edge_backward_q(g.csr, q, k, e, da, ds, ss, ctx.act, ctx.act_param, need[3], out=dq_buf,
+                                    scale_da_inplace=True)
+            edge_backward_k(g.csc, q, k, e, da, None, ss, ctx.act, ctx.act_param, out=k)
+            del da
+            q.copy_(dq_buf)
+            del dq_buf
+            dqk = qk
+        else:
+            dqk = (torch.empty if ldp == d else torch.zeros)(qk.shape, dtype=qk.dtype, device=qk.device)
+            dq, dk = dqk[:, :d], dqk[:, ldp:ldp + d]
+            # the dQ pass leaves dA scaled by the destination coefficient (in place: `da` is ours)
+            _, de = edge_backward_q(g.csr, q, k, e, da, ds, ss, ctx.act, ctx.act_param, need[3], out=dq,
+                                    scale_da_inplace=True)
+            edge_backward_k(g.csc, q, k, e, da, None, ss, ctx.act, ctx.act_param, out=dk)
+            del da
+        del q, k, qk
         dw_qk = gemm.linear_wgrad(dqk, feat, w_qk.dtype) if need[1] else None
         db_qk = gemm.column_sum(dqk, w_qk.dtype) if (need[2] and ctx.has_bias[0]) else None
-        dfeat = gemm.linear_dgrad(dqk, w_qk.to(qk.dtype)).to(feat.dtype) if need[0] else None
+        dfeat = gemm.linear_dgrad(dqk, w_qk.to(dqk.dtype)).to(feat.dtype) if need[0] else None
         return dfeat, dw_qk, db_qk, de, dw_r, db_r, None, None, None, None, None, None
 
 

@@ -417,6 +417,29 @@ def test_contexts_no_grad_eval_deterministic_autocast():
     assert not hasattr(g, "ndata")
 
 
+@pytest.mark.parametrize("dtype,d", [(torch.float32, 64), (torch.bfloat16, 128), (torch.float32, 75)])
+def test_recompute_lean_backward_is_bit_identical(dtype, d):
+    """recompute_qk (auto for tables > 4 GiB): [Q|K] is re-made in backward and dK is written in place over K
+    (function.py `lean`); every gradient must equal the keep-everything path bit for bit"""
+    n, e = 400, 6000
+    src, dst = rand_graph(n, e, 31, hub=7)
+    g = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
+    assert g.csc.n_chunks > 0 and g.csr.n_chunks > 0            # long rows in both walks
+    torch.manual_seed(0)
+    layer = SIREConv(32, 3, d, 48, nn.LeakyReLU(0.2), agg_type="sym").to(DEV).to(dtype)
+    x = torch.randn(n, 32, device=DEV, dtype=dtype)
+    ef = torch.randn(e, 3, device=DEV, dtype=dtype)
+    gout = torch.randn(n, 48, device=DEV, dtype=dtype)
+    res = []
+    for recompute in (False, True):
+        layer.recompute_qk = recompute
+        xg, eg = x.clone().requires_grad_(True), ef.clone().requires_grad_(True)
+        out = layer(g, xg, eg)
+        res.append([out] + list(torch.autograd.grad(out, [xg, eg] + list(layer.parameters()), gout)))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
 # ---- full-size properties (sizes the oracle cannot finish quickly) -----------------------------------
 def test_arxiv_sized_properties():
     src, dst, n = synth.arxiv_like(seed=0, device=DEV)
