@@ -213,6 +213,13 @@ size_t sirgcn_colsum_workspace_bytes(int32_t n);
 int sirgcn_colsum(const void *x, int64_t ld, int64_t m, int32_t n, int32_t dtype, float *out, void *workspace,
                   size_t workspace_bytes, void *stream);
 
+/* dst[r, 0..row_bytes) = src[r, 0..row_bytes) for r < rows: row tables with different row pitches (one half of a
+ * [N, 2·ld] buffer <-> a [N, ld] buffer), 128-bit vectors at HBM speed.  row_bytes, both pitches and both base
+ * pointers must be multiples of 16.  Used by the memory-lean backward of the layer (no reference counterpart: the
+ * reference keeps every [E, d] intermediate instead). */
+int sirgcn_copy_rows(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
+                     int64_t row_bytes, int64_t rows, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * Split path for arbitrary (non-elementwise) σ, agg_type 'max'/'min', and the
  * SIRConvBase/SIREConvBase classes (conv.py:47, :137-221; dictionary-lookup/model.py:17).

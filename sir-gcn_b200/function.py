@@ -28,6 +28,24 @@ def _alloc_table(n, d, dtype, device, zero=False):
     return buf[:, :d]
 
 
+def copy_rows(dst, src):
+    """dst[:, :] = src for two row tables of the same shape and dtype whose rows are 16-byte aligned (any row
+    strides): sirgcn_copy_rows when the row is a whole number of 16-byte vectors, torch otherwise"""
+    es = src.element_size()
+    rb = src.shape[1] * es
+    ok = (src.is_cuda and dst.is_cuda and src.dtype == dst.dtype and src.shape == dst.shape and src.dim() == 2
+          and src.stride(1) == 1 and dst.stride(1) == 1 and rb % 16 == 0 and src.data_ptr() % 16 == 0
+          and dst.data_ptr() % 16 == 0 and (src.stride(0) * es) % 16 == 0 and (dst.stride(0) * es) % 16 == 0)
+    if not ok or src.shape[0] == 0:
+        return dst.copy_(src)
+    with torch.cuda.device(src.device):
+        rc = _lib.lib().sirgcn_copy_rows(_lib.ptr(dst), C.c_int64(dst.stride(0) * es), _lib.ptr(src),
+                                         C.c_int64(src.stride(0) * es), C.c_int64(rb), C.c_int64(src.shape[0]),
+                                         _lib.stream_ptr(src.device))
+    _lib.check(rc, "sirgcn_copy_rows")
+    return dst
+
+
 def _table_ok(t):
     es = t.element_size()
     if t.dim() != 2 or t.stride(1) != 1 or t.data_ptr() % 16:
@@ -239,7 +257,8 @@ class SIRLayerFunction(torch.autograd.Function):
                                     scale_da_inplace=True)
             edge_backward_k(g.csc, q, k, e, da, None, ss, ctx.act, ctx.act_param, out=k)
             del da
-            q.copy_(dq_buf)
+            ldq = _pad_cols(d, qk.dtype)                    # whole 16-byte vectors, zero padding included
+            copy_rows(qk[:, :ldq], dq_buf.as_strided((dq_buf.shape[0], ldq), (dq_buf.stride(0), 1)))
             del dq_buf
             dqk = qk
         else:
