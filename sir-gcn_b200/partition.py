@@ -474,14 +474,17 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                 _mark("fwd:edge")
                 out = gemm.linear_forward(a, w_r.to(dt), b_r)
             _mark("fwd:out")
-            saved += [h, k_all, a]
-            state.append(dict(k_sl=k_sl, q_sl=q_sl, q_full=q_full, q_h=q_h, d=d, ld=ld))
+            # intermediates live on ctx (not in save_for_backward) so that backward can drop layer l's tables as soon
+            # as layer l is done — the whole stack is ONE autograd node, whose saved tensors would otherwise all live
+            # until its backward returns (at 2 GPUs that is the difference between fitting the 2 B-edge graph or not)
+            state.append(dict(k_sl=k_sl, q_sl=q_sl, q_full=q_full, q_h=q_h, d=d, ld=ld, k_all=k_all, a=a,
+                              h=None if l == 0 else h))
             h = out
         if not train:
             for lease in leases:
                 lease.release()
             return h
-        ctx.save_for_backward(*saved, *weights, feat_full)
+        ctx.save_for_backward(feat, feat_full, *weights)
         ctx.leases, ctx.state, ctx.part, ctx.cfgs, ctx.backend, ctx.L = leases, state, part, cfgs, backend, L
         return h
 
@@ -489,7 +492,7 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
     def backward(ctx, gout):
         L, part, be, leases, state = ctx.L, ctx.part, ctx.backend, ctx.leases, ctx.state
         tensors = ctx.saved_tensors
-        saved, weights, feat_full = tensors[:3 * L], tensors[3 * L:-1], tensors[-1]
+        feat0, feat_full, weights = tensors[0], tensors[1], tensors[2:]
         tr = part.transport()
         n = part.n_local
         need = ctx.needs_input_grad
@@ -497,10 +500,10 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
         grads = [[None] * 5 for _ in range(L)]       # fp32 partials of this rank, reduced at the end
         g = gout
         for l in reversed(range(L)):
-            feat, k_all, a = saved[3 * l:3 * l + 3]
+            st, lease = state[l], leases[l]
+            feat, k_all, a = (feat0 if l == 0 else st["h"]), st["k_all"], st["a"]
             w_q, b_q, w_k, w_r, b_r = weights[5 * l:5 * l + 5]
             agg_type, act, act_param = ctx.cfgs[l]
-            st, lease = state[l], leases[l]
             d, ld, q_sl, k_sl = st["d"], st["ld"], st["q_sl"], st["k_sl"]
             dt, dev = q_sl.local.dtype, q_sl.local.device
             adt = torch.float64 if dt == torch.float64 else torch.float32
@@ -555,8 +558,9 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             be.backward_k(part.csc, qf, k, None, daf, None, part.scale_cols_rows(agg_type), act, act_param, out=dk)
             _mark("bwd:edge_k")
             lease.release()
-            st["q_full"] = None
-            del da_full, daf, qf, kf, k_all
+            del da_full, daf, qf, kf, k_all, q, k, da, a, dq, dk, da_sl, q_sl, k_sl, da_h
+            for key in ("q_full", "q_h", "k_all", "a", "k_sl", "q_sl"):
+                st[key] = None
             featd = feat.to(dt)
             if wneed[l][0] or wneed[l][2]:
                 dw_qk = (dqk.t() @ featd).to(adt)                          # [2·ld, d_in]
@@ -569,6 +573,8 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                 w_cat[:d].copy_(w_q)
                 w_cat[ld:ld + d].copy_(w_k)
                 g = gemm.linear_dgrad(dqk, w_cat)
+            st["h"] = None
+            del feat, featd, dqk
             _mark("bwd:grads")
         # weight gradients of all layers: fp32 partials of every rank in ONE flat all-reduce
         live = [(l, i, t) for l in range(L) for i, t in enumerate(grads[l]) if t is not None and wneed[l][i]]
@@ -581,7 +587,7 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                 out_w[5 * l + i] = flat[off:off + t.numel()].view(t.shape).to(weights[5 * l + i].dtype)
                 off += t.numel()
         _mark("bwd:allreduce")
-        dfeat = g.to(saved[0].dtype) if need[0] else None
+        dfeat = g.to(feat0.dtype) if need[0] else None
         return (dfeat, None, None, None, None, None, *out_w)
 
 
