@@ -204,3 +204,45 @@ def test_oracle_reproduces_golden():
         torch.testing.assert_close(dfeat, c["dfeat"], rtol=1e-6, atol=1e-6)
         for x, y in zip(csr_csc_ref(c["src"], c["dst"], m["n"])[:6], c["csr"][:6]):
             assert torch.equal(x, y)
+
+
+# ---- two independent restatements agree: torch ops + autograd  vs  plain C loops + hand-written derivative -----------
+@pytest.mark.parametrize("agg", ["sum", "mean", "sym"])
+@pytest.mark.parametrize("act", ["relu", "leaky", "gelu", "identity"])
+def test_c_restatement_matches_torch_oracle(agg, act):
+    from oracle import edge_stage_c
+    g = torch.Generator().manual_seed(7)
+    n, e, d = 60, 700, 9
+    src, dst = torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)
+    dst[:200] = 4                                            # a hub, multi-edges and self loops included
+    dst[dst == 11] = 12                                      # node 11: no in-edges
+    sigma = {"relu": nn.ReLU(), "leaky": nn.LeakyReLU(0.2), "gelu": nn.GELU(), "identity": nn.Identity()}[act]
+    layer = RefSIREConv(5, 3, d, 7, sigma, agg_type=agg).double()
+    x = torch.randn(n, 5, generator=g, dtype=torch.float64)
+    ef = torch.randn(e, 3, generator=g, dtype=torch.float64)
+    graph = RefGraph(src, dst, n)
+    # the torch oracle, opened up at the edge stage: A is the input of linear_relation
+    seen = {}
+    hook = layer.linear_relation.register_forward_hook(lambda m, inp, out: seen.setdefault("a", inp[0]))
+    q = layer.linear_query(x).detach().requires_grad_(True)
+    k = layer.linear_key(x).detach().requires_grad_(True)
+    pe = layer.linear_edge(ef).detach().requires_grad_(True)
+
+    class Const(nn.Module):                                  # the projections, cut out of the autograd graph
+        def __init__(self, t):
+            super().__init__()
+            self.t = t
+
+        def forward(self, _):
+            return self.t
+
+    layer.linear_query, layer.linear_key, layer.linear_edge = Const(q), Const(k), Const(pe)
+    layer(graph, x, ef)
+    hook.remove()
+    a_t = seen["a"]
+    da = torch.randn(n, d, generator=g, dtype=torch.float64)
+    dq_t, dk_t, de_t = torch.autograd.grad(a_t, (q, k, pe), da)
+    a_c, dq_c, dk_c, de_c = edge_stage_c(src, dst, n, q, k, pe, act, 0.2, agg, da)
+    for got, want in ((a_c, a_t), (dq_c, dq_t), (dk_c, dk_t), (de_c, de_t)):
+        torch.testing.assert_close(got, want.detach(), rtol=1e-12, atol=1e-12)
+    assert torch.equal(a_c[11], torch.zeros(d, dtype=torch.float64))
