@@ -214,6 +214,7 @@ def transport_name(args):
     return {"peer": "copy-engine pulls from IPC-mapped peer slices",
             "push": "copy-engine pushes into IPC-mapped peer tables",
             "pushsm": "a fan-out push kernel writing into IPC-mapped peer tables",
+            "pushtma": "a TMA bulk-copy fan-out kernel writing into IPC-mapped peer tables",
             "collective": "NCCL all-gathers"}[kind]
 
 
@@ -498,7 +499,7 @@ def main():
                     help="N>1: do not gather the node features ahead of the layers (layer 1 gathers K and Q in line)")
     ap.add_argument("--e2e-input-gather", action="store_true",
                     help="N>1: the e2e leg also gathers every step's node features over NVLink behind their H2D copy")
-    ap.add_argument("--transport", default="auto", choices=["auto", "push", "pushsm", "peer", "collective"],
+    ap.add_argument("--transport", default="auto", choices=["auto", "push", "pushsm", "pushtma", "peer", "collective"],
                     help="N>1: how row tables travel between ranks (partition.RowPartition.transport)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":

@@ -272,6 +272,11 @@ int sirgcn_peer_copy(void *dst, const void *src, size_t bytes, void *stream);
  * (HOST array of device pointers: peer mappings and/or local buffers) by a kernel of at most n_ctas CTAs —
  * posted writes over NVLink, for when the copy engines' many-to-many rate is the limit. */
 int sirgcn_peer_push(const void *src, void *const *dsts, int32_t n_dst, size_t bytes, int32_t n_ctas, void *stream);
+/* The same fan-out with TMA bulk copies: one elected thread per CTA streams the slice global -> shared ring ->
+ * every target (cp.async.bulk), so the transfer costs a shared-memory ring per CTA and no issue slots.
+ * status[0] (device int32) is set to 2 if a copy never lands (bounded wait, nothing hangs). */
+int sirgcn_peer_push_tma(const void *src, void *const *dsts, int32_t n_dst, size_t bytes, int32_t n_ctas,
+                         int32_t *status, void *stream);
 int sirgcn_peer_barrier(uint32_t *const *pads, int32_t world, int32_t rank, uint32_t epoch, uint64_t timeout_ns,
                         int32_t *status, void *stream);
 

@@ -75,10 +75,102 @@ __global__ void __launch_bounds__(512) peer_push_kernel(const uint4 *__restrict_
     }
 }
 
+// ---- TMA fan-out: one elected thread per CTA moves the slice with bulk copies ----------------------------------
+// global (own slice) --cp.async.bulk--> shared ring --cp.async.bulk--> every target.  No issue slots and no registers
+// are spent on the data; the CTA costs its shared-memory ring (kTmaStages x kTmaChunk) and one resident warp.
+constexpr int kTmaChunk = 32 * 1024;
+constexpr int kTmaStages = 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__global__ void __launch_bounds__(32) peer_push_tma_kernel(const char *__restrict__ src, PushTargets tg, int n_dst,
+                                                            size_t bytes, int *status) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) unsigned long long full[kTmaStages];
+    if (threadIdx.x != 0) return;
+    for (int s = 0; s < kTmaStages; ++s)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&full[s])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const size_t n_chunks = (bytes + kTmaChunk - 1) / kTmaChunk;
+    const size_t first = blockIdx.x, step = gridDim.x;
+    auto chunk_bytes = [&](size_t c) { return (uint32_t)min((size_t)kTmaChunk, bytes - c * kTmaChunk); };
+    auto load = [&](size_t c, int s) {
+        const uint32_t bar = smem_addr(&full[s]), dst = smem_addr(ring + (size_t)s * kTmaChunk), nb = chunk_bytes(c);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src + c * kTmaChunk), "r"(nb), "r"(bar) : "memory");
+    };
+    // Software pipeline.  Loads run kTmaAhead chunks ahead of the stores.  The stage that chunk it+kTmaAhead is loaded
+    // into was last read by the store group of chunk it+kTmaAhead-kTmaStages; when iteration `it` starts, groups up to
+    // it-1 are committed, so at most kTmaStages-kTmaAhead-1 groups may still be reading their stage.
+    constexpr int kTmaAhead = 2;
+    static_assert(kTmaStages - kTmaAhead - 1 >= 1, "stores must be allowed to overlap");
+    size_t issued = first;
+    int n_issued = 0;
+    for (; n_issued < kTmaAhead && issued < n_chunks; ++n_issued, issued += step) load(issued, n_issued);
+    int it = 0;
+    for (size_t c = first; c < n_chunks; c += step, ++it) {
+        const int s = it % kTmaStages;
+        const uint32_t parity = (uint32_t)(it / kTmaStages) & 1u;
+        if (issued < n_chunks) {
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kTmaStages - kTmaAhead - 1) : "memory");
+            load(issued, n_issued % kTmaStages);
+            ++n_issued;
+            issued += step;
+        }
+        unsigned spins = 0;
+        while (!mbar_try_wait(smem_addr(&full[s]), parity)) {
+            if (++spins > (1u << 26)) {                     // a copy that never lands: report, do not hang
+                atomicExch(status, 2);
+                return;
+            }
+        }
+        const uint32_t from = smem_addr(ring + (size_t)s * kTmaChunk), nb = chunk_bytes(c);
+        for (int t = 0; t < n_dst; ++t)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(reinterpret_cast<char *>(tg.dst[t]) + c * kTmaChunk), "r"(from), "r"(nb) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // every store has been written, not only read
+}
+
 }  // namespace
 }  // namespace sirgcn
 
 extern "C" {
+
+int sirgcn_peer_push_tma(const void *src, void *const *dsts, int32_t n_dst, size_t bytes, int32_t n_ctas,
+                         int32_t *status, void *stream) {
+    using namespace sirgcn;
+    SIRGCN_CHECK_ARG(n_dst >= 1 && n_dst <= SIRGCN_PEER_MAX_WORLD && dsts && status, "bad n_dst=%d/dsts/status", n_dst);
+    SIRGCN_CHECK_ARG(bytes % 16 == 0 && aligned16(src), "src/bytes must be 16-byte aligned");
+    if (bytes == 0) return SIRGCN_OK;
+    PushTargets tg{};
+    for (int t = 0; t < n_dst; ++t) {
+        SIRGCN_CHECK_ARG(dsts[t] && aligned16(dsts[t]), "target %d is NULL or unaligned", t);
+        tg.dst[t] = dsts[t];
+    }
+    const size_t n_chunks = (bytes + kTmaChunk - 1) / kTmaChunk;
+    const int grid = (int)std::min<size_t>((size_t)std::max(1, n_ctas), n_chunks);
+    const int smem = kTmaStages * kTmaChunk;
+    static std::atomic<bool> configured{false};
+    if (!configured.load(std::memory_order_relaxed)) {
+        SIRGCN_CUDA(cudaFuncSetAttribute(peer_push_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured.store(true, std::memory_order_relaxed);
+    }
+    peer_push_tma_kernel<<<grid, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const char *>(src), tg, n_dst, bytes, status);
+    SIRGCN_LAUNCHED();
+    return SIRGCN_OK;
+}
 
 int sirgcn_peer_push(const void *src, void *const *dsts, int32_t n_dst, size_t bytes, int32_t n_ctas, void *stream) {
     using namespace sirgcn;

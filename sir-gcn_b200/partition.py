@@ -144,7 +144,7 @@ class PushTransport:
         from . import peer
         self.pool = peer.PeerPool(part.group)
         self.mode = mode
-        self.kind = "push" if mode == "ce" else "pushsm"
+        self.kind = {"ce": "push", "sm": "pushsm", "tma": "pushtma"}[mode]
         self._fulls = {}
 
     def acquire(self, rows, ld, dtype, device, zero):
@@ -318,8 +318,8 @@ class RowPartition:
     # ---- transport --------------------------------------------------------------------------------------------
     def transport(self):
         """how row tables travel between the ranks (CUDA tensors of an NCCL group of one node, except "collective"):
-        "push" / "pushsm" (every rank writes its slice into every peer's IPC-mapped gathered table, by copy engines /
-        by a fan-out kernel), "peer" (copy-engine pulls from IPC-mapped peer slices) or "collective"
+        "push" / "pushsm" / "pushtma" (every rank writes its slice into every peer's IPC-mapped gathered table, by
+        copy engines / a fan-out kernel / a TMA bulk-copy fan-out kernel), "peer" (copy-engine pulls from IPC-mapped peer slices) or "collective"
         (torch.distributed all-gathers).  "auto" picks AUTO_TRANSPORT when it applies; the environment variable
         SIRGCN_TRANSPORT overrides."""
         if self._transport is None:
@@ -331,6 +331,7 @@ class RowPartition:
                 kind = AUTO_TRANSPORT if on_gpu else "collective"
             self._transport = {"peer": lambda: PeerTransport(self), "push": lambda: PushTransport(self, "ce"),
                                "pushsm": lambda: PushTransport(self, "sm"),
+                               "pushtma": lambda: PushTransport(self, "tma"),
                                "collective": lambda: CollectiveTransport(self)}[kind]()
         return self._transport
 

@@ -207,8 +207,10 @@ class PeerPool:
 
     def check(self):
         """host-side: raise if any barrier gave up waiting for a peer (synchronises the device)"""
-        if int(self._status.item()) != 0:
-            raise RuntimeError("sirgcn_peer_barrier timed out: a peer rank never arrived")
+        code = int(self._status.item())
+        if code != 0:
+            raise RuntimeError("sirgcn_peer_barrier timed out: a peer rank never arrived" if code == 1 else
+                               "sirgcn_peer_push_tma: a bulk copy never landed")
 
     def ensure_writable(self, sl: PeerSlice):
         """call before the producer overwrites sl.local: fences the peers' pulls of its previous contents"""
@@ -271,7 +273,8 @@ class PeerPool:
     def push(self, src, pf: PeerFull, lo=0, hi=None, mode="ce"):
         """rows [lo, hi) of this rank's slice `src` ([rows, ld], any local tensor that stays alive until the handle has
         been waited for) -> rows rank*rows + lo.. of EVERY rank's table.  mode "ce": one copy-engine write per peer;
-        "sm": one fan-out kernel of a few CTAs (sirgcn_peer_push).  Two barriers frame the transfer, neither blocks
+        "sm": one fan-out kernel of a few CTAs (sirgcn_peer_push); "tma": the same with TMA bulk copies issued by one
+        thread per CTA (sirgcn_peer_push_tma).  Two barriers frame the transfer, neither blocks
         the current stream: "every rank is done reading the table's previous contents" (skipped when a barrier has
         been issued since the table was released) and "every rank's rows have landed".  Returns a PushHandle."""
         hi = pf.rows if hi is None else hi
@@ -290,7 +293,7 @@ class PeerPool:
         src_ptr = src.data_ptr() + lo * src.stride(0) * src.element_size()
         assert src.stride(0) == pf.ld and src.stride(1) == 1
         events = []
-        if mode == "sm":
+        if mode in ("sm", "tma"):
             st = self.push_stream
             st.wait_event(free_ev)
             st.wait_event(ready)
@@ -298,8 +301,14 @@ class PeerPool:
             targets.append(pf.base + off)
             arr = (C.c_void_p * len(targets))(*targets)
             with torch.cuda.device(self.device):
-                rc = self.lib.sirgcn_peer_push(C.c_void_p(src_ptr), arr, C.c_int32(len(targets)), C.c_size_t(nbytes),
-                                               C.c_int32(self.push_ctas), C.c_void_p(st.cuda_stream))
+                if mode == "tma":
+                    rc = self.lib.sirgcn_peer_push_tma(C.c_void_p(src_ptr), arr, C.c_int32(len(targets)),
+                                                       C.c_size_t(nbytes), C.c_int32(self.push_ctas),
+                                                       C.c_void_p(self._status.data_ptr()), C.c_void_p(st.cuda_stream))
+                else:
+                    rc = self.lib.sirgcn_peer_push(C.c_void_p(src_ptr), arr, C.c_int32(len(targets)),
+                                                   C.c_size_t(nbytes), C.c_int32(self.push_ctas),
+                                                   C.c_void_p(st.cuda_stream))
             _lib.check(rc, "sirgcn_peer_push")
             ev = torch.cuda.Event()
             ev.record(st)

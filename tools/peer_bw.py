@@ -82,6 +82,9 @@ def main():
     for ctas in (8, 16, 32, 64, 128):
         pool.push_ctas = ctas
         res[f"sm_push_{ctas}ctas"] = run(push("sm"), pf.local)
+    for ctas in (4, 8, 16, 32):
+        pool.push_ctas = ctas
+        res[f"tma_push_{ctas}ctas"] = run(push("tma"), pf.local)
     pool.check()
     if rank == 0:
         print(json.dumps(res), flush=True)
