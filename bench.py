@@ -199,8 +199,12 @@ def workload_config(args, w):
             "nodes": n, "edges": e, "d_in": w["d_in"], "d_hidden": w["d"], "layers": w["layers"],
             "agg": w["agg"], "activation": w["act"], "table_dtype": w["dtype"],
             "partition": "single GPU" if args.gpus == 1 else
-            f"1-D destination rows over {args.gpus} GPUs; row tables travel by {transport_name(args)}; layer l+1's K "
-            f"gathered in {args.chunks} destination chunks under layer l's walk, Q and dA gathers under the other walks"
+            f"1-D destination rows over {args.gpus} GPUs; row tables travel by {transport_name(args)}; "
+            + (f"layer l+1's INPUT rows gathered in {args.chunks} destination chunks under layer l's walk and its K/Q "
+               f"tables projected locally by every rank, dA gathered under the dQ walk"
+               if args.gather == "inputs" else
+               f"layer l+1's K gathered in {args.chunks} destination chunks under layer l's walk, Q and dA gathers "
+               f"under the other walks")
             + ("" if args.no_input_gather else "; node features of all ranks gathered ahead of the layers (layer 1 projects K/Q locally)"),
             "l2": "inputs >> 126 MB L2, no flush" if e * w["d"] * (4 if w["dtype"] == "f32" else 2) > (1 << 30)
             else "L2 flushed (256 MiB write) between timed steps"}
@@ -278,7 +282,7 @@ def run_gpu(args, w):
         full_of = {}
 
         def run_layers(h):
-            return partition.partitioned_sirconv_stack(list(layers), part, h, chunks=args.chunks,
+            return partition.partitioned_sirconv_stack(list(layers), part, h, chunks=args.chunks, gather=args.gather,
                                                        feat_full=full_of.get(h.data_ptr()))
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
@@ -495,6 +499,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunks", type=int, default=4,
                     help="N>1: destination chunks of the cross-layer K prefetch (1 = gather each K table whole)")
+    ap.add_argument("--gather", default="projections", choices=["inputs", "projections"],
+                    help="N>1: what travels between layers — the K and Q projections (default) or the layer input "
+                         "(every rank then projects the whole K/Q tables locally)")
     ap.add_argument("--no-input-gather", action="store_true",
                     help="N>1: do not gather the node features ahead of the layers (layer 1 gathers K and Q in line)")
     ap.add_argument("--e2e-input-gather", action="store_true",

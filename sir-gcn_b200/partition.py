@@ -392,23 +392,30 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
     row-partitioned graph as ONE autograd node — the unit that can hide the table traffic (module docstring):
     same arithmetic per row as SIRLayerFunction; every rank ends with the full-graph weight gradients.
 
-    apply(feat, part, cfgs, chunks, backend, feat_full, *weights):  cfgs[l] = (agg_type, act, act_param);
-    weights = (w_q, b_q, w_k, w_r, b_r) per layer, flattened.  feat_full (optional, no gradient): the input rows of
-    ALL ranks (RowPartition.all_gather_rows); the first layer then projects its whole K table (and, in backward, its
-    whole Q table) locally and two of the table transfers disappear."""
+    apply(feat, part, cfgs, opts, backend, feat_full, *weights):  cfgs[l] = (agg_type, act, act_param);
+    weights = (w_q, b_q, w_k, w_r, b_r) per layer, flattened; opts = {"chunks": destination chunks of the cross-layer
+    prefetch, "gather": "inputs" | "projections"}.
+    "inputs": what travels for layer l+1 is its INPUT H_l+1 (= layer l's output rows, sent chunk by chunk under layer
+    l's walk); every rank then projects the whole K table (forward) and Q table (backward) of layer l+1 locally —
+    one table transfer per layer instead of two, for two 50 M-row GEMMs (4 ms each against a 17-19 ms transfer).
+    "projections": K_l+1 is projected per chunk and travels under layer l's walk, Q_l travels in backward.
+    feat_full (optional, no gradient): the input rows of ALL ranks (RowPartition.all_gather_rows); the first layer
+    then projects its tables locally in either mode."""
 
     @staticmethod
-    def forward(ctx, feat, part: RowPartition, cfgs, chunks, backend, feat_full, *weights):
+    def forward(ctx, feat, part: RowPartition, cfgs, opts, backend, feat_full, *weights):
         L = len(cfgs)
         W = [weights[5 * l:5 * l + 5] for l in range(L)]
         n, dt, dev = part.n_local, feat.dtype, feat.device
         tr = part.transport()
         leases = [_Lease(tr) for _ in range(L)]     # what layer l holds until its backward has run
         train = any(ctx.needs_input_grad)
-        chunks = max(1, int(chunks)) if part.world > 1 else 1
-        saved, state = [], []
+        chunks = max(1, int(opts.get("chunks", 4))) if part.world > 1 else 1
+        gather_inputs = opts.get("gather", "projections") == "inputs"
+        state = []
         h = feat
-        pre = None                          # (k_sl, k_all, [handles]) of the current layer when prefetched
+        pre = None                          # (k_sl, k_all, [handles]) of the current layer when K was prefetched
+        h_full, h_handles = feat_full, []   # this layer's input rows of ALL ranks (+ their arrival), when they travel
         for l in range(L):
             lease = leases[l]
             w_q, b_q, w_k, w_r, b_r = W[l]
@@ -416,10 +423,13 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             d = w_q.shape[0]
             ld = F_._pad_cols(d, dt)
             _mark("fwd:start")
-            if l == 0 and feat_full is not None:
-                k_all = torch.empty((feat_full.shape[0], ld), dtype=dt, device=dev) if ld == d else \
-                    torch.zeros((feat_full.shape[0], ld), dtype=dt, device=dev)
-                _project(feat_full.to(dt), w_k.to(dt), None, k_all, feat_full.shape[0], d, ld)
+            if h_full is not None:
+                for hnd in h_handles:
+                    hnd.wait()
+                _mark("fwd:wait_H")
+                k_all = torch.empty((h_full.shape[0], ld), dtype=dt, device=dev) if ld == d else \
+                    torch.zeros((h_full.shape[0], ld), dtype=dt, device=dev)
+                _project(h_full.to(dt), w_k.to(dt), None, k_all, h_full.shape[0], d, ld)
                 k_sl = _CollectiveSlice(k_all[part.rank * part.n_pad:(part.rank + 1) * part.n_pad])
                 k_handles = []
             elif pre is None:
@@ -435,7 +445,7 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             # Q of the remote destinations is consumed by the backward CSC pass only.  The last layer's travels behind
             # its own forward walk; an earlier layer's is left for the backward pass (the ports carry K_l+1 now).
             q_full = q_h = None
-            if train and l == L - 1:
+            if train and l == L - 1 and h_full is None:
                 q_full = tr.new_full(q_sl, lease)
                 q_h = tr.gather(q_sl, q_full)
             q, kf = _table(q_sl.local, n, d), _table(k_all, k_all.shape[0], d)
@@ -445,7 +455,30 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             for hnd in k_handles:
                 hnd.wait()
             _mark("fwd:wait_K")
-            if l + 1 < L:
+            h_full_next, h_handles_next = None, []
+            if l + 1 < L and gather_inputs:
+                # walk in destination chunks; chunk c of this layer's OUTPUT (the next layer's input) is sent to every
+                # rank while chunk c+1 is walked
+                do = w_r.shape[0]
+                ldo = F_._pad_cols(do, dt)
+                out_sl = leases[l + 1].add(tr.acquire(part.n_pad, ldo, dt, dev, zero=ldo != do))
+                hn_all = tr.new_full(out_sl, leases[l + 1])
+                for lo, hi, rows in part.row_chunks(chunks):
+                    if rows is not None:
+                        top = lo + rows.n_rows
+                        backend.forward(rows, q[lo:top], kf, None, None if ds is None else ds[lo:top], ss, act,
+                                        act_param, out=a[lo:top])
+                        if ldo == do:
+                            gemm.linear_forward(a[lo:top], w_r.to(dt), b_r, out=out_sl.local[lo:top])
+                        else:
+                            out_sl.local[lo:top, :do].copy_(gemm.linear_forward(a[lo:top], w_r.to(dt), b_r))
+                    if hi > lo:
+                        h_handles_next.append(tr.gather(out_sl, hn_all, lo, hi))
+                out = out_sl.local[:n, :do]
+                h_full_next = hn_all[:, :do]
+                a._sirgcn_padded = True
+                _mark("fwd:edge")
+            elif l + 1 < L:
                 # walk in destination chunks; chunk c of the NEXT layer's K is produced and sent while c+1 is walked
                 w_kn = W[l + 1][2].to(dt)
                 dn = w_kn.shape[0]
@@ -479,8 +512,8 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             # as layer l is done — the whole stack is ONE autograd node, whose saved tensors would otherwise all live
             # until its backward returns (at 2 GPUs that is the difference between fitting the 2 B-edge graph or not)
             state.append(dict(k_sl=k_sl, q_sl=q_sl, q_full=q_full, q_h=q_h, d=d, ld=ld, k_all=k_all, a=a,
-                              h=None if l == 0 else h))
-            h = out
+                              h=None if l == 0 else h, h_full=None if l == 0 else h_full, has_full=h_full is not None))
+            h, h_full, h_handles = out, h_full_next, h_handles_next
         if not train:
             for lease in leases:
                 lease.release()
@@ -503,6 +536,7 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
         for l in reversed(range(L)):
             st, lease = state[l], leases[l]
             feat, k_all, a = (feat0 if l == 0 else st["h"]), st["k_all"], st["a"]
+            h_full = (feat_full if l == 0 else st["h_full"]) if st["has_full"] else None
             w_q, b_q, w_k, w_r, b_r = weights[5 * l:5 * l + 5]
             agg_type, act, act_param = ctx.cfgs[l]
             d, ld, q_sl, k_sl = st["d"], st["ld"], st["q_sl"], st["k_sl"]
@@ -538,11 +572,12 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             _mark("bwd:dA")
             be.backward_q(part.csr, q, kf, None, da, None, ss, act, act_param, False, out=dq)
             _mark("bwd:edge_q")
-            if l == 0 and feat_full is not None and st["q_h"] is None:
-                # the first layer's Q table of ALL destinations is a projection of the gathered input: made here
-                qf_buf = (torch.empty if ld == d else torch.zeros)((feat_full.shape[0], ld), dtype=dt, device=dev)
-                _project(feat_full.to(dt), w_q.to(dt), b_q, qf_buf, feat_full.shape[0], d, ld)
+            if h_full is not None:
+                # the Q table of ALL destinations is a projection of the layer input that every rank holds: made here
+                qf_buf = (torch.empty if ld == d else torch.zeros)((h_full.shape[0], ld), dtype=dt, device=dev)
+                _project(h_full.to(dt), w_q.to(dt), b_q, qf_buf, h_full.shape[0], d, ld)
                 st["q_full"] = qf_buf
+                del qf_buf
             else:
                 if st["q_h"] is None:       # not prefetched by the layer above (cannot happen for l = L-1)
                     st["q_full"] = tr.new_full(q_sl, lease)
@@ -550,7 +585,7 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                 st["q_h"].wait()
             da_h.wait()
             _mark("bwd:wait_Q_dA")
-            if l > 1 or (l == 1 and feat_full is None):
+            if l > 0 and not state[l - 1]["has_full"]:
                 # the layer below needs its Q table next: it travels under this CSC walk
                 sb = state[l - 1]
                 sb["q_full"] = tr.new_full(sb["q_sl"], leases[l - 1])
@@ -558,9 +593,8 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             qf = _table(st["q_full"], st["q_full"].shape[0], d)
             be.backward_k(part.csc, qf, k, None, daf, None, part.scale_cols_rows(agg_type), act, act_param, out=dk)
             _mark("bwd:edge_k")
-            lease.release()
-            del da_full, daf, qf, kf, k_all, q, k, da, a, dq, dk, da_sl, q_sl, k_sl, da_h
-            for key in ("q_full", "q_h", "k_all", "a", "k_sl", "q_sl"):
+            del da_full, daf, qf, kf, k_all, q, k, da, a, dq, dk, da_sl, q_sl, k_sl, da_h, h_full
+            for key in ("q_full", "q_h", "k_all", "a", "k_sl", "q_sl", "h_full"):
                 st[key] = None
             featd = feat.to(dt)
             if wneed[l][0] or wneed[l][2]:
@@ -576,6 +610,7 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                 g = gemm.linear_dgrad(dqk, w_cat)
             st["h"] = None
             del feat, featd, dqk
+            lease.release()                 # after the last reader of this layer's slices has been enqueued
             _mark("bwd:grads")
         # weight gradients of all layers: fp32 partials of every rank in ONE flat all-reduce
         live = [(l, i, t) for l in range(L) for i, t in enumerate(grads[l]) if t is not None and wneed[l][i]]
@@ -605,11 +640,17 @@ def _layer_args(layer):
 
 
 def partitioned_sirconv_stack(layers, part: RowPartition, feat_loc, chunks=4, backend=CudaEdgeBackend,
-                              feat_full=None):
+                              feat_full=None, gather="projections"):
     """Run consecutive `SIRConv` layers (output of one = input of the next, nothing in between) on this rank's rows
-    of a partitioned graph as one autograd node; `chunks` = destination chunks of the cross-layer K prefetch.
+    of a partitioned graph as one autograd node; `chunks` = destination chunks of the cross-layer prefetch.
     `feat_loc` = rows [part.lo, part.hi) of the node features; `feat_full` (optional) = the rows of all ranks,
-    part.all_gather_rows(feat_loc) — an input gathered ahead of time instead of two projections gathered in line."""
+    part.all_gather_rows(feat_loc) — an input gathered ahead of time instead of two projections gathered in line.
+    `gather`: what travels between layers — "projections" (the K and Q tables; default) or "inputs" (the layer
+    input, projected locally by every rank: one table transfer per layer instead of two, paid for with two
+    whole-table GEMMs per layer that nothing hides — worth it only where the link, not the dependency chain, is the
+    limit)."""
+    if gather not in ("inputs", "projections"):
+        raise ValueError(f"gather must be 'inputs' or 'projections', not {gather!r}")
     if feat_loc.shape[0] != part.n_local:
         raise ValueError(f"feat_loc has {feat_loc.shape[0]} rows, this rank owns {part.n_local}")
     if feat_full is not None and feat_full.shape[0] != part.world * part.n_pad:
@@ -621,9 +662,10 @@ def partitioned_sirconv_stack(layers, part: RowPartition, feat_loc, chunks=4, ba
         c, w = _layer_args(layer)
         cfgs.append(c)
         weights += list(w)
-    return PartitionedSIRStackFunction.apply(feat_loc, part, tuple(cfgs), chunks, backend, feat_full, *weights)
+    opts = {"chunks": chunks, "gather": gather}
+    return PartitionedSIRStackFunction.apply(feat_loc, part, tuple(cfgs), opts, backend, feat_full, *weights)
 
 
 def partitioned_sirconv(layer, part: RowPartition, feat_loc, backend=CudaEdgeBackend):
     """Run one `SIRConv` (sum / mean / sym, elementwise σ, no dropout) on this rank's rows of a partitioned graph."""
-    return partitioned_sirconv_stack([layer], part, feat_loc, 1, backend)
+    return partitioned_sirconv_stack([layer], part, feat_loc, 1, backend, gather="projections")

@@ -108,7 +108,7 @@ def _reference(src, dst, n, layer, x, gout):
     return out.detach(), grads
 
 
-def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, ret):
+def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, gather, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -135,7 +135,7 @@ def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, ret):
         if use_full:
             assert x_full.shape[0] == world * part.n_pad and torch.equal(x_full[:n], x)
         out = partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks, backend=TorchEdgeBackend,
-                                                  feat_full=x_full)
+                                                  feat_full=x_full, gather=gather)
         grads = torch.autograd.grad(out, [xl] + [p for l in layers for p in l.parameters()], gout[part.lo:part.hi])
         # degree coefficients are fp32 by design (the kernels read fp32 scales): 1e-6; pure sums: 1e-10
         tol = dict(rtol=1e-10, atol=1e-12) if agg == "sum" else dict(rtol=1e-6, atol=1e-7)
@@ -144,21 +144,24 @@ def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, ret):
         for a, b in zip(grads[1:], g_ref[1:]):          # every rank holds the FULL-graph weight gradient
             ok &= torch.allclose(a, b, **tol)
         with torch.no_grad():
-            ok &= torch.allclose(partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks,
+            ok &= torch.allclose(partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks, gather=gather,
                                                                      backend=TorchEdgeBackend, feat_full=x_full), out)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("agg,act,n_layers,chunks,use_full", [
-    ("sum", "relu", 1, 1, False), ("mean", "leaky", 2, 3, False), ("sym", "gelu", 3, 2, False),
-    ("sym", "leaky", 1, 1, True), ("mean", "relu", 2, 4, True)])
-def test_partition_gloo_world2_matches_single_process(agg, act, n_layers, chunks, use_full):
+@pytest.mark.parametrize("agg,act,n_layers,chunks,use_full,gather", [
+    ("sum", "relu", 1, 1, False, "projections"), ("mean", "leaky", 2, 3, False, "projections"),
+    ("sym", "gelu", 3, 2, False, "projections"), ("sym", "leaky", 1, 1, True, "projections"),
+    ("mean", "relu", 2, 4, True, "projections"),
+    ("sym", "gelu", 3, 2, False, "inputs"), ("mean", "leaky", 2, 4, True, "inputs"), ("sum", "relu", 2, 1, False, "inputs")])
+def test_partition_gloo_world2_matches_single_process(agg, act, n_layers, chunks, use_full, gather):
     world, port = 2, _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_gloo_worker, args=(world, port, agg, act, n_layers, chunks, use_full, ret), nprocs=world, join=True)
+        mp.spawn(_gloo_worker, args=(world, port, agg, act, n_layers, chunks, use_full, gather, ret), nprocs=world,
+                 join=True)
         assert dict(ret) == {0: True, 1: True}
 
 
@@ -249,19 +252,23 @@ def _nccl_worker(rank, world, port, transport, chunks, barrier, ret):
         params = [p for l in layers for p in l.parameters()]
         xl = x[part.lo:part.hi].to(dev).requires_grad_(True)
         for it in range(3):     # repeated steps recycle the peer slices (overwrite fences) and must stay bit-identical
-            out = partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks)
+            out = partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks, gather="projections")
             grads = torch.autograd.grad(out, [xl] + params, gout[part.lo:part.hi].to(dev))
             if it == 0:
                 first = [out.clone()] + [g.clone() for g in grads]
             else:
                 assert all(torch.equal(a, b) for a, b in zip(first, [out] + list(grads))), "step not repeatable"
         with torch.no_grad():   # inference: nothing is held for a backward that never comes
-            assert torch.equal(partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks), first[0])
-        # the input gathered ahead of time (layer 1 projects its K / Q tables locally): same result
+            assert torch.equal(partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks,
+                                                                   gather="projections"), first[0])
+        # the input gathered ahead of time (layer 1 projects its K / Q tables locally), and layer inputs instead of
+        # projections travelling between the layers: same result
         x_full = part.all_gather_rows(xl.detach())
-        out_f = partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks, feat_full=x_full)
-        grads_f = torch.autograd.grad(out_f, [xl] + params, gout[part.lo:part.hi].to(dev))
-        assert all(_rel(a, b) < 1e-6 for a, b in zip([out_f] + list(grads_f), first))
+        for kw in (dict(feat_full=x_full, gather="projections"), dict(feat_full=x_full, gather="inputs"),
+                   dict(gather="inputs")):
+            out_f = partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks, **kw)
+            grads_f = torch.autograd.grad(out_f, [xl] + params, gout[part.lo:part.hi].to(dev))
+            assert all(_rel(a, b) < 1e-6 for a, b in zip([out_f] + list(grads_f), first)), kw
         # layer by layer (no cross-layer prefetch, whole-table projections) agrees with the stack (the library SGEMM
         # may pick another kernel for a row chunk, so not bit for bit in fp32)
         h = xl
