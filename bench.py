@@ -205,6 +205,7 @@ def workload_config(args, w):
                if args.gather == "inputs" else
                f"layer l+1's K gathered in {args.chunks} destination chunks under layer l's walk, Q and dA gathers "
                f"under the other walks")
+            + ("" if args.bwd_chunks <= 1 else f"; dK walk in {args.bwd_chunks} source chunks with the next dA table travelling under it")
             + ("" if args.no_input_gather else "; node features of all ranks gathered ahead of the layers (layer 1 projects K/Q locally)"),
             "l2": "inputs >> 126 MB L2, no flush" if e * w["d"] * (4 if w["dtype"] == "f32" else 2) > (1 << 30)
             else "L2 flushed (256 MiB write) between timed steps"}
@@ -283,6 +284,7 @@ def run_gpu(args, w):
 
         def run_layers(h):
             return partition.partitioned_sirconv_stack(list(layers), part, h, chunks=args.chunks, gather=args.gather,
+                                                       bwd_chunks=args.bwd_chunks,
                                                        feat_full=full_of.get(h.data_ptr()))
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
@@ -499,6 +501,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunks", type=int, default=4,
                     help="N>1: destination chunks of the cross-layer K prefetch (1 = gather each K table whole)")
+    ap.add_argument("--bwd-chunks", type=int, default=1,
+                    help="N>1: source chunks of the dK walk under which the layer below's dA table travels (1 = off)")
     ap.add_argument("--gather", default="projections", choices=["inputs", "projections"],
                     help="N>1: what travels between layers — the K and Q projections (default) or the layer input "
                          "(every rank then projects the whole K/Q tables locally)")

@@ -231,6 +231,21 @@ class RowPartition:
             self._row_chunks[chunks] = got
         return got
 
+    def col_chunks(self, chunks):
+        """the same cut of the local SOURCE rows (out-CSC), for the chunked dK walk of the backward pass"""
+        got = self._row_chunks.get(("csc", chunks))
+        if got is None:
+            step = (self.n_pad + chunks - 1) // chunks
+            got = []
+            for c in range(chunks):
+                lo, hi = min(self.n_pad, c * step), min(self.n_pad, (c + 1) * step)
+                top = min(hi, self.n_local)
+                rows = self.csc if (chunks == 1 and top == self.n_local) else \
+                    (self.csc.slice_rows(lo, top) if top > lo else None)
+                got.append((lo, hi, rows))
+            self._row_chunks[("csc", chunks)] = got
+        return got
+
     # ---- construction ---------------------------------------------------------------------------------
     @classmethod
     def from_csr_csc(cls, csr: CompressedRows, csc: CompressedRows, num_nodes, rank, world, group=None,
@@ -520,6 +535,7 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             return h
         ctx.save_for_backward(feat, feat_full, *weights)
         ctx.leases, ctx.state, ctx.part, ctx.cfgs, ctx.backend, ctx.L = leases, state, part, cfgs, backend, L
+        ctx.bwd_chunks = max(1, int(opts.get("bwd_chunks", 1))) if part.world > 1 else 1
         return h
 
     @staticmethod
@@ -533,6 +549,7 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
         wneed = [need[6 + 5 * l:11 + 5 * l] for l in range(L)]
         grads = [[None] * 5 for _ in range(L)]       # fp32 partials of this rank, reduced at the end
         g = gout
+        prepared = None                 # (da_sl, da_full, [handles]) of the current layer when the layer above sent it
         for l in reversed(range(L)):
             st, lease = state[l], leases[l]
             feat, k_all, a = (feat0 if l == 0 else st["h"]), st["k_all"], st["a"]
@@ -545,19 +562,24 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             g = g.to(dt)
             g = g if g.stride(-1) == 1 else g.contiguous()
             _mark("bwd:start")
-            # dA, scaled by the destination coefficient BEFORE it travels: the CSC pass then needs no scale lookup
-            da_sl = lease.add(tr.acquire(part.n_pad, ld, dt, dev, zero=ld != d))
-            da = _table(da_sl.local, n, d)
-            if n:
-                if ld == d:
-                    gemm.linear_dgrad(g, w_r.to(dt), out=da)
-                else:
-                    da.copy_(gemm.linear_dgrad(g, w_r.to(dt)))
             ds, ss = part.scales_rows(agg_type)
-            if ds is not None:
-                da.mul_(ds[:n].to(dt).unsqueeze(1))
-            da_full = tr.new_full(da_sl, lease)
-            da_h = tr.gather(da_sl, da_full)                              # travels while dQ is computed
+            if prepared is None:
+                # dA, scaled by the destination coefficient BEFORE it travels: the CSC pass then needs no scale lookup
+                da_sl = lease.add(tr.acquire(part.n_pad, ld, dt, dev, zero=ld != d))
+                da = _table(da_sl.local, n, d)
+                if n:
+                    if ld == d:
+                        gemm.linear_dgrad(g, w_r.to(dt), out=da)
+                    else:
+                        da.copy_(gemm.linear_dgrad(g, w_r.to(dt)))
+                if ds is not None:
+                    da.mul_(ds[:n].to(dt).unsqueeze(1))
+                da_full = tr.new_full(da_sl, lease)
+                da_handles = [tr.gather(da_sl, da_full)]                  # travels while dQ is computed
+            else:
+                da_sl, da_full, da_handles = prepared                     # sent chunk by chunk under the dK walk above
+                prepared = None
+                da = _table(da_sl.local, n, d)
             if wneed[l][3]:
                 grads[l][3] = (g.t() @ a).to(adt)
             if wneed[l][4] and b_r is not None:
@@ -583,7 +605,8 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                     st["q_full"] = tr.new_full(q_sl, lease)
                     st["q_h"] = tr.gather(q_sl, st["q_full"])
                 st["q_h"].wait()
-            da_h.wait()
+            for hnd in da_handles:
+                hnd.wait()
             _mark("bwd:wait_Q_dA")
             if l > 0 and not state[l - 1]["has_full"]:
                 # the layer below needs its Q table next: it travels under this CSC walk
@@ -591,9 +614,47 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                 sb["q_full"] = tr.new_full(sb["q_sl"], leases[l - 1])
                 sb["q_h"] = tr.gather(sb["q_sl"], sb["q_full"])
             qf = _table(st["q_full"], st["q_full"].shape[0], d)
-            be.backward_k(part.csc, qf, k, None, daf, None, part.scale_cols_rows(agg_type), act, act_param, out=dk)
+            sc_rows = part.scale_cols_rows(agg_type)
+            w_cat = None
+            if l > 0 or need[0]:
+                w_cat = (torch.zeros if ld != d else torch.empty)((2 * ld, w_q.shape[1]), dtype=dt, device=dev)
+                w_cat[:d].copy_(w_q)
+                w_cat[ld:ld + d].copy_(w_k)
+            g = None
+            if l > 0 and ctx.bwd_chunks > 1:
+                # dK walk in source chunks: chunk c of dH_l = [dQ|dK][c]·[W_Q;W_K] gives chunk c of the layer below's dA,
+                # which travels while chunk c+1 is walked — the layer below then starts with its dA table in place
+                sb, lb = state[l - 1], leases[l - 1]
+                w_rb = weights[5 * (l - 1) + 3].to(dt)
+                db_, ldb = sb["d"], sb["ld"]
+                dsb = part.scales_rows(ctx.cfgs[l - 1][0])[0]
+                dab_sl = lb.add(tr.acquire(part.n_pad, ldb, dt, dev, zero=ldb != db_))
+                dab_full = tr.new_full(dab_sl, lb)
+                g = torch.empty((n, w_q.shape[1]), dtype=dt, device=dev)
+                handles = []
+                for lo, hi, rows in part.col_chunks(ctx.bwd_chunks):
+                    if rows is not None:
+                        top = lo + rows.n_rows
+                        be.backward_k(rows, qf, k[lo:top], None, daf, None, None if sc_rows is None else sc_rows[lo:top],
+                                      act, act_param, out=dk[lo:top])
+                        gemm.linear_dgrad(dqk[lo:top], w_cat, out=g[lo:top])
+                        dab = dab_sl.local[lo:top, :db_]
+                        if ldb == db_:
+                            gemm.linear_dgrad(g[lo:top], w_rb, out=dab)
+                        else:
+                            dab.copy_(gemm.linear_dgrad(g[lo:top], w_rb))
+                        if dsb is not None:
+                            dab.mul_(dsb[lo:top].to(dt).unsqueeze(1))
+                    if hi > lo:
+                        handles.append(tr.gather(dab_sl, dab_full, lo, hi))
+                prepared = (dab_sl, dab_full, handles)
+                del dab_sl, dab_full
+            else:
+                be.backward_k(part.csc, qf, k, None, daf, None, sc_rows, act, act_param, out=dk)
+                if w_cat is not None:
+                    g = gemm.linear_dgrad(dqk, w_cat)
             _mark("bwd:edge_k")
-            del da_full, daf, qf, kf, k_all, q, k, da, a, dq, dk, da_sl, q_sl, k_sl, da_h, h_full
+            del da_full, daf, qf, kf, k_all, q, k, da, a, dq, dk, da_sl, q_sl, k_sl, da_handles, h_full
             for key in ("q_full", "q_h", "k_all", "a", "k_sl", "q_sl", "h_full"):
                 st[key] = None
             featd = feat.to(dt)
@@ -602,12 +663,6 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                 grads[l][0], grads[l][2] = dw_qk[:d], dw_qk[ld:ld + d]
             if wneed[l][1] and b_q is not None:
                 grads[l][1] = gemm.column_sum(dqk, adt)[:d]
-            g = None
-            if l > 0 or need[0]:
-                w_cat = (torch.zeros if ld != d else torch.empty)((2 * ld, w_q.shape[1]), dtype=dt, device=dev)
-                w_cat[:d].copy_(w_q)
-                w_cat[ld:ld + d].copy_(w_k)
-                g = gemm.linear_dgrad(dqk, w_cat)
             st["h"] = None
             del feat, featd, dqk
             lease.release()                 # after the last reader of this layer's slices has been enqueued
@@ -640,7 +695,7 @@ def _layer_args(layer):
 
 
 def partitioned_sirconv_stack(layers, part: RowPartition, feat_loc, chunks=4, backend=CudaEdgeBackend,
-                              feat_full=None, gather="projections"):
+                              feat_full=None, gather="projections", bwd_chunks=1):
     """Run consecutive `SIRConv` layers (output of one = input of the next, nothing in between) on this rank's rows
     of a partitioned graph as one autograd node; `chunks` = destination chunks of the cross-layer prefetch.
     `feat_loc` = rows [part.lo, part.hi) of the node features; `feat_full` (optional) = the rows of all ranks,
@@ -648,7 +703,10 @@ def partitioned_sirconv_stack(layers, part: RowPartition, feat_loc, chunks=4, ba
     `gather`: what travels between layers — "projections" (the K and Q tables; default) or "inputs" (the layer
     input, projected locally by every rank: one table transfer per layer instead of two, paid for with two
     whole-table GEMMs per layer that nothing hides — worth it only where the link, not the dependency chain, is the
-    limit)."""
+    limit).
+    `bwd_chunks` > 1: the dK walk of every layer but the first runs in that many source chunks, and chunk c of the
+    layer below's dA table (dH[c]·W_R, scaled) travels under the walk of chunk c+1 — the layer below then starts its
+    dQ walk with no transfer competing for the SMs and its dA table already in place."""
     if gather not in ("inputs", "projections"):
         raise ValueError(f"gather must be 'inputs' or 'projections', not {gather!r}")
     if feat_loc.shape[0] != part.n_local:
@@ -662,7 +720,7 @@ def partitioned_sirconv_stack(layers, part: RowPartition, feat_loc, chunks=4, ba
         c, w = _layer_args(layer)
         cfgs.append(c)
         weights += list(w)
-    opts = {"chunks": chunks, "gather": gather}
+    opts = {"chunks": chunks, "gather": gather, "bwd_chunks": bwd_chunks}
     return PartitionedSIRStackFunction.apply(feat_loc, part, tuple(cfgs), opts, backend, feat_full, *weights)
 
 

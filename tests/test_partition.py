@@ -108,7 +108,7 @@ def _reference(src, dst, n, layer, x, gout):
     return out.detach(), grads
 
 
-def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, gather, ret):
+def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, gather, bwd_chunks, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -135,7 +135,7 @@ def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, gather
         if use_full:
             assert x_full.shape[0] == world * part.n_pad and torch.equal(x_full[:n], x)
         out = partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks, backend=TorchEdgeBackend,
-                                                  feat_full=x_full, gather=gather)
+                                                  feat_full=x_full, gather=gather, bwd_chunks=bwd_chunks)
         grads = torch.autograd.grad(out, [xl] + [p for l in layers for p in l.parameters()], gout[part.lo:part.hi])
         # degree coefficients are fp32 by design (the kernels read fp32 scales): 1e-6; pure sums: 1e-10
         tol = dict(rtol=1e-10, atol=1e-12) if agg == "sum" else dict(rtol=1e-6, atol=1e-7)
@@ -151,17 +151,18 @@ def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, gather
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("agg,act,n_layers,chunks,use_full,gather", [
-    ("sum", "relu", 1, 1, False, "projections"), ("mean", "leaky", 2, 3, False, "projections"),
-    ("sym", "gelu", 3, 2, False, "projections"), ("sym", "leaky", 1, 1, True, "projections"),
-    ("mean", "relu", 2, 4, True, "projections"),
-    ("sym", "gelu", 3, 2, False, "inputs"), ("mean", "leaky", 2, 4, True, "inputs"), ("sum", "relu", 2, 1, False, "inputs")])
-def test_partition_gloo_world2_matches_single_process(agg, act, n_layers, chunks, use_full, gather):
+@pytest.mark.parametrize("agg,act,n_layers,chunks,use_full,gather,bwd_chunks", [
+    ("sum", "relu", 1, 1, False, "projections", 1), ("mean", "leaky", 2, 3, False, "projections", 1),
+    ("sym", "gelu", 3, 2, False, "projections", 3), ("sym", "leaky", 1, 1, True, "projections", 2),
+    ("mean", "relu", 2, 4, True, "projections", 4),
+    ("sym", "gelu", 3, 2, False, "inputs", 1), ("mean", "leaky", 2, 4, True, "inputs", 3),
+    ("sum", "relu", 2, 1, False, "inputs", 2)])
+def test_partition_gloo_world2_matches_single_process(agg, act, n_layers, chunks, use_full, gather, bwd_chunks):
     world, port = 2, _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_gloo_worker, args=(world, port, agg, act, n_layers, chunks, use_full, gather, ret), nprocs=world,
-                 join=True)
+        mp.spawn(_gloo_worker, args=(world, port, agg, act, n_layers, chunks, use_full, gather, bwd_chunks, ret),
+                 nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
 
 
@@ -265,7 +266,7 @@ def _nccl_worker(rank, world, port, transport, chunks, barrier, ret):
         # projections travelling between the layers: same result
         x_full = part.all_gather_rows(xl.detach())
         for kw in (dict(feat_full=x_full, gather="projections"), dict(feat_full=x_full, gather="inputs"),
-                   dict(gather="inputs")):
+                   dict(gather="inputs"), dict(feat_full=x_full, bwd_chunks=3), dict(gather="inputs", bwd_chunks=2)):
             out_f = partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks, **kw)
             grads_f = torch.autograd.grad(out_f, [xl] + params, gout[part.lo:part.hi].to(dev))
             assert all(_rel(a, b) < 1e-6 for a, b in zip([out_f] + list(grads_f), first)), kw
