@@ -168,6 +168,7 @@ class SIRConvBase(nn.Module):
         super().__init__()
         _check_agg(agg_type)
         self._agg_type = agg_type
+        self._agg_func = "sum" if agg_type == "sym" else agg_type   # name of the DGL builtin (conv.py:154)
         self._message_func = message_func
 
     def forward(self, graph, feat, efeat=None):
