@@ -166,6 +166,33 @@ def test_partition_gloo_world2_matches_single_process(agg, act, n_layers, chunks
         assert dict(ret) == {0: True, 1: True}
 
 
+@pytest.mark.parametrize("n_layers,gather,bwd_chunks,use_full", [(1, "projections", 1, False), (2, "projections", 1, True),
+                                                                 (3, "inputs", 2, False)])
+def test_partition_world1_host_logic(n_layers, gather, bwd_chunks, use_full):
+    """a single rank (no process group): the stack function degenerates to the plain layer stack"""
+    n = 41
+    src, dst, ref, x, gout = _case(9, n, 500, 6, 12, 6, "leaky", "sym")
+    torch.manual_seed(3)
+    refs = [ref] + [RefSIRConv(6, 12, 6, ACTS["leaky"](), agg_type="sym").double() for _ in range(n_layers - 1)]
+    out_ref, g_ref = _reference(src, dst, n, refs, x, gout)
+    c = csr_csc_ref(src, dst, n)
+    part = partition.RowPartition.from_csr_csc(CompressedRows(c[0], c[1], None), CompressedRows(c[3], c[4], None), n, 0, 1)
+    layers = []
+    for r in refs:
+        layer = SIRConv(6, 12, 6, ACTS["leaky"](), agg_type="sym").double()
+        layer.load_state_dict(r.state_dict())
+        layers.append(layer)
+    xl = x.clone().requires_grad_(True)
+    out = partition.partitioned_sirconv_stack(layers, part, xl, chunks=3, backend=TorchEdgeBackend, gather=gather,
+                                              bwd_chunks=bwd_chunks,
+                                              feat_full=part.all_gather_rows(xl.detach()) if use_full else None)
+    grads = torch.autograd.grad(out, [xl] + [p for l in layers for p in l.parameters()], gout)
+    tol = dict(rtol=1e-6, atol=1e-7)
+    assert torch.allclose(out, out_ref, **tol)
+    for a, b in zip(grads, g_ref):
+        assert torch.allclose(a, b, **tol)
+
+
 def test_partition_bounds_cover_every_row_once():
     for n, world in [(10, 3), (37, 2), (5, 8), (16, 4)]:
         rows = []
