@@ -215,7 +215,7 @@ def transport_name(args):
     kind = os.environ.get("SIRGCN_TRANSPORT", args.transport)
     if kind == "auto":
         from sirgcn_b200 import partition
-        kind = partition.AUTO_TRANSPORT
+        kind = partition.auto_transport(args.gpus)
     return {"peer": "copy-engine pulls from IPC-mapped peer slices",
             "push": "copy-engine pushes into IPC-mapped peer tables",
             "pushsm": "a fan-out push kernel writing into IPC-mapped peer tables",

@@ -335,7 +335,7 @@ class RowPartition:
         """how row tables travel between the ranks (CUDA tensors of an NCCL group of one node, except "collective"):
         "push" / "pushsm" / "pushtma" (every rank writes its slice into every peer's IPC-mapped gathered table, by
         copy engines / a fan-out kernel / a TMA bulk-copy fan-out kernel), "peer" (copy-engine pulls from IPC-mapped peer slices) or "collective"
-        (torch.distributed all-gathers).  "auto" picks AUTO_TRANSPORT when it applies; the environment variable
+        (torch.distributed all-gathers).  "auto" picks auto_transport(world) when it applies; the environment variable
         SIRGCN_TRANSPORT overrides."""
         if self._transport is None:
             import os
@@ -343,7 +343,7 @@ class RowPartition:
             if kind == "auto":
                 on_gpu = self.csr.indptr.is_cuda and self.world > 1 and dist.is_initialized() \
                     and dist.get_backend(self.group) == "nccl"
-                kind = AUTO_TRANSPORT if on_gpu else "collective"
+                kind = auto_transport(self.world) if on_gpu else "collective"
             self._transport = {"peer": lambda: PeerTransport(self), "push": lambda: PushTransport(self, "ce"),
                                "pushsm": lambda: PushTransport(self, "sm"),
                                "pushtma": lambda: PushTransport(self, "tma"),
@@ -372,7 +372,14 @@ class RowPartition:
         return t
 
 
-AUTO_TRANSPORT = "collective"
+def auto_transport(world):
+    """From 4 GPUs up: copy-engine pushes into IPC-mapped peer tables.  Alone they move a table more slowly than NCCL
+    (537 vs 665 GB/s per rank at 8 GPUs, profiles/r01_peer_bw_n8.json) but they take no SM, and in the step every
+    transfer but one runs under an edge walk: NCCL's kernels slow those walks by 30-45 % (forward 17.6 vs 12.1 ms,
+    dQ 18.9 vs 13.9 ms at 8 GPUs).  At 2 GPUs the transfers are small, NCCL is kept: its gathered tables come from
+    the caching allocator, which matters when the 2 B-edge graph leaves ~35 GiB free per GPU."""
+    return "push" if world >= 4 else "collective"
+
 
 
 # bench.py sets this to a list to collect (label, CUDA event) marks on the compute stream (phase breakdown)
