@@ -25,7 +25,6 @@ import ctypes as C
 
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
 from . import _lib, gemm
 from . import function as F_
