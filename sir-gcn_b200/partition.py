@@ -343,10 +343,18 @@ class RowPartition:
                 on_gpu = self.csr.indptr.is_cuda and self.world > 1 and dist.is_initialized() \
                     and dist.get_backend(self.group) == "nccl"
                 kind = auto_transport(self.world) if on_gpu else "collective"
-            self._transport = {"peer": lambda: PeerTransport(self), "push": lambda: PushTransport(self, "ce"),
-                               "pushsm": lambda: PushTransport(self, "sm"),
-                               "pushtma": lambda: PushTransport(self, "tma"),
-                               "collective": lambda: CollectiveTransport(self)}[kind]()
+            make = {"peer": lambda: PeerTransport(self), "push": lambda: PushTransport(self, "ce"),
+                    "pushsm": lambda: PushTransport(self, "sm"), "pushtma": lambda: PushTransport(self, "tma"),
+                    "collective": lambda: CollectiveTransport(self)}[kind]
+            requested = os.environ.get("SIRGCN_TRANSPORT", self._transport_kind)
+            try:
+                self._transport = make()
+            except RuntimeError as exc:     # peer-memory setup failed on some rank (agreed on by all ranks, peer.py)
+                if requested != "auto":
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory transport unavailable ({exc}); using torch.distributed all-gathers")
+                self._transport = CollectiveTransport(self)
         return self._transport
 
     def all_gather_rows(self, local, out=None):

@@ -131,23 +131,44 @@ class PeerPool:
 
     # ---- allocation ---------------------------------------------------------------------------------------------
     def _alloc_mapped(self, nbytes):
-        """collective: (own device pointer, [peer r's allocation mapped here or None])"""
+        """collective: (own device pointer, [peer r's allocation mapped here or None]).  A failure on ANY rank
+        (allocation, IPC export or mapping) is agreed on by all ranks before anybody raises, so that the caller can
+        fall back to another transport on every rank at once instead of leaving the others in a collective."""
         handle = (C.c_ubyte * 64)()
         base = C.c_void_p()
+        err = None
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.sirgcn_peer_alloc(C.c_size_t(nbytes), C.byref(base), handle), "sirgcn_peer_alloc")
+            rc = self.lib.sirgcn_peer_alloc(C.c_size_t(nbytes), C.byref(base), handle)
+        if rc != 0:
+            err = f"sirgcn_peer_alloc failed (rc={rc}): {self.lib.sirgcn_last_error().decode()}"
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        dist.all_gather_object(handles, None if err else bytes(handle), group=self.group)
         peers = []
         for r, h in enumerate(handles):
-            if r == self.rank:
+            if r == self.rank or h is None or err:
                 peers.append(None)
                 continue
             p = C.c_void_p()
             buf = (C.c_ubyte * 64).from_buffer_copy(h)
             with torch.cuda.device(self.device):
-                _lib.check(self.lib.sirgcn_peer_open(buf, C.byref(p)), "sirgcn_peer_open")
-            peers.append(p.value)
+                rc = self.lib.sirgcn_peer_open(buf, C.byref(p))
+            if rc != 0:
+                err = f"sirgcn_peer_open failed (rc={rc}): {self.lib.sirgcn_last_error().decode()}"
+                peers.append(None)
+            else:
+                peers.append(p.value)
+        if any(h is None for h in handles) and not err:
+            err = "a peer rank could not allocate or export its buffer"
+        bad = torch.tensor([1 if err else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.group)
+        if int(bad.item()):
+            for p in peers:
+                if p:
+                    self.lib.sirgcn_peer_close(C.c_void_p(p))
+            dist.barrier(group=self.group)          # nobody frees memory a peer still has mapped
+            if base.value:
+                self.lib.sirgcn_peer_free(base)
+            raise RuntimeError("peer-memory setup failed on at least one rank" + (f": {err}" if err else ""))
         return base.value, peers
 
     def acquire(self, rows, ld, dtype) -> PeerSlice:
