@@ -481,6 +481,9 @@ def run_gpu(args, w):
         }
         emit(line)
     if world > 1:
+        pool = getattr(part.transport(), "pool", None)
+        if pool is not None:
+            pool.check()            # a device-side barrier or bulk copy that gave up must not pass silently
         dist.destroy_process_group()
 
 
