@@ -444,6 +444,11 @@ def run_gpu(args, w):
     ms_e2e = timed(e2e_step, max(1, min(args.steps, 3)))
     h2d = x_host.numel() * x_host.element_size()
 
+    if world > 1:
+        pool = getattr(part.transport(), "pool", None)
+        if pool is not None:
+            pool.check()            # a device-side barrier or bulk copy that gave up must not pass silently: no line
+
     # ---- CPU baseline on rank 0 (bounded sample) --------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -481,9 +486,6 @@ def run_gpu(args, w):
         }
         emit(line)
     if world > 1:
-        pool = getattr(part.transport(), "pool", None)
-        if pool is not None:
-            pool.check()            # a device-side barrier or bulk copy that gave up must not pass silently
         dist.destroy_process_group()
 
 
