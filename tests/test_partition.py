@@ -158,12 +158,23 @@ def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, gather
     ("sym", "gelu", 3, 2, False, "inputs", 1), ("mean", "leaky", 2, 4, True, "inputs", 3),
     ("sum", "relu", 2, 1, False, "inputs", 2)])
 def test_partition_gloo_world2_matches_single_process(agg, act, n_layers, chunks, use_full, gather, bwd_chunks):
-    world, port = 2, _free_port()
+    _run_gloo(2, agg, act, n_layers, chunks, use_full, gather, bwd_chunks)
+
+
+@pytest.mark.parametrize("agg,act,n_layers,chunks,use_full,gather,bwd_chunks", [
+    ("mean", "relu", 2, 5, True, "projections", 2), ("sym", "leaky", 2, 2, False, "inputs", 3)])
+def test_partition_gloo_world3_ragged_last_rank(agg, act, n_layers, chunks, use_full, gather, bwd_chunks):
+    """37 nodes over 3 ranks: n_pad = 13, the last rank owns 11 rows, and with 5 chunks some chunks of it are empty"""
+    _run_gloo(3, agg, act, n_layers, chunks, use_full, gather, bwd_chunks)
+
+
+def _run_gloo(world, agg, act, n_layers, chunks, use_full, gather, bwd_chunks):
+    port = _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
         mp.spawn(_gloo_worker, args=(world, port, agg, act, n_layers, chunks, use_full, gather, bwd_chunks, ret),
                  nprocs=world, join=True)
-        assert dict(ret) == {0: True, 1: True}
+        assert dict(ret) == {r: True for r in range(world)}
 
 
 @pytest.mark.parametrize("n_layers,gather,bwd_chunks,use_full", [(1, "projections", 1, False), (2, "projections", 1, True),
