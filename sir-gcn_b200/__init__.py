@@ -6,7 +6,7 @@ The directory is named ``sir-gcn_b200``; import it as ``sirgcn_b200`` through th
 from . import _lib
 from .conv import SIRConv, SIREConv, SIRConvBase, SIREConvBase, classify_activation
 from .function import EdgeAggregate, GatherAdd, SegmentReduce
-from .graph import CompressedRows, Graph, as_graph
+from .graph import CompressedRows, DropEdge, Graph, as_graph
 
-__all__ = ["SIRConv", "SIREConv", "SIRConvBase", "SIREConvBase", "Graph", "CompressedRows", "as_graph",
+__all__ = ["SIRConv", "SIREConv", "SIRConvBase", "SIREConvBase", "Graph", "CompressedRows", "DropEdge", "as_graph",
            "EdgeAggregate", "GatherAdd", "SegmentReduce", "classify_activation"]

@@ -256,6 +256,22 @@ class Graph:
         return None, None
 
 
+class DropEdge:
+    """Call-compatible stand-in for the reference's `DropEdge(p)(graph, efeats) -> (graph, efeats)`
+    (/root/reference/models/utils.py:96-102, a dgl.transforms.DropEdge that also subsets the edge features), on this
+    package's converted graphs: no rebuild, no sort (Graph.drop_edges), and p = 0 hands the graph back untouched."""
+
+    def __init__(self, p=0.5):
+        self.p = float(p)
+
+    def __call__(self, graph, efeats=None):
+        g = as_graph(graph)
+        sub, keep = g.drop_edges(self.p)
+        if efeats is None or sub is g:
+            return sub, efeats
+        return sub, efeats[keep]
+
+
 _dgl_cache = weakref.WeakKeyDictionary()
 
 

@@ -236,6 +236,11 @@ def test_drop_edges_layer_matches_oracle_on_kept_edges():
     out_r = ref.double()(RefGraph(src[keep_c], dst[keep_c], n), x.double(), ef[keep_c].double())
     out_g = gpu(sub, x.to(DEV), ef.to(DEV)[keep])
     assert rel_err(out_g, out_r) < FP32_RTOL
+    # the reference's call shape: DropEdge(p)(graph, efeats) -> (graph, efeats)   (models/utils.py:96-102)
+    g0, e0 = sirgcn_b200.DropEdge(0.0)(g, ef)
+    assert g0 is g and e0 is ef
+    g1, e1 = sirgcn_b200.DropEdge(0.5)(g, ef.to(DEV))
+    assert e1.shape[0] == g1.num_edges() < e
 
 
 # ---- whole layers --------------------------------------------------------------------------------
