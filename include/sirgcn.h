@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIRGCN_ABI_VERSION 7
+#define SIRGCN_ABI_VERSION 8
 
 /* element types of feature tables (accumulation is always fp32) */
 enum { SIRGCN_F32 = 0, SIRGCN_BF16 = 1, SIRGCN_F16 = 2 };
@@ -60,8 +60,10 @@ uint64_t sirgcn_launch_count(void);
  * Long-row schedule (rows with degree > long_threshold are split into chunks of
  * long_threshold edges so that hubs are spread over many warps):
  *   sched_*_long_rows[cap_long], sched_*_long_first[cap_long + 1 ... see below],
- *   sched_*_chunk_lrow[cap_chunks], sched_*_chunk_beg[cap_chunks], counts[4] =
- *   {n_long_in, n_chunks_in, n_long_out, n_chunks_out} (device int32).
+ *   sched_*_chunk_lrow[cap_chunks], sched_*_chunk_beg[cap_chunks], counts[5] =
+ *   {n_long_in, n_chunks_in, n_long_out, n_chunks_out, bad_ids} (device int32).  bad_ids != 0: some src/dst id was
+ *   outside [0, num_nodes) — such ids are clamped so that nothing indexes out of bounds, and the caller must
+ *   reject the graph once it has read the counts (DGL raises for such a graph as well).
  *   cap_long = E/long_threshold + 1, cap_chunks = 2*E/long_threshold + 2.
  * workspace: sirgcn_csr_build_workspace_bytes(E, N) bytes of device scratch.
  */
@@ -85,7 +87,7 @@ int sirgcn_csr_build(const int32_t *src, const int32_t *dst, int64_t num_edges, 
                      float *in_norm, float *out_norm, float *inv_in_deg,
                      int32_t long_threshold,
                      const sirgcn_schedule *sched_in, const sirgcn_schedule *sched_out,
-                     int32_t *counts /* [4] device */,
+                     int32_t *counts /* [5] device */,
                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* One compressed-row structure from (key, other) pairs: rows = key values in [0, num_rows), stable
@@ -260,7 +262,8 @@ int sirgcn_segment_minmax_bwd(int64_t num_pos, const int32_t *rsel, const void *
  * r's flag pad, uint32[SIRGCN_PEER_MAX_WORLD] inside a peer allocation; the kernel stores `epoch` into slot
  * `rank` of every peer's pad (release, system scope) and waits until every slot of its own pad has reached
  * `epoch` (acquire); epochs must grow by one per call on every rank.  If a peer has not arrived after
- * `timeout_ns` the kernel gives up and sets status[0] = 1 (device int32) instead of hanging. */
+ * `timeout_ns` the kernel sets status[0] = 1 (device int32) and TRAPS: the process's context is dead and every
+ * later CUDA call fails, so no kernel ever reads a table that was not gathered (nothing hangs, nothing is silent). */
 #define SIRGCN_IPC_HANDLE_BYTES 64
 #define SIRGCN_PEER_MAX_WORLD 32
 int sirgcn_peer_alloc(size_t bytes, void **dev_ptr, void *ipc_handle /* [SIRGCN_IPC_HANDLE_BYTES] out */);
@@ -274,7 +277,7 @@ int sirgcn_peer_copy(void *dst, const void *src, size_t bytes, void *stream);
 int sirgcn_peer_push(const void *src, void *const *dsts, int32_t n_dst, size_t bytes, int32_t n_ctas, void *stream);
 /* The same fan-out with TMA bulk copies: one elected thread per CTA streams the slice global -> shared ring ->
  * every target (cp.async.bulk), so the transfer costs a shared-memory ring per CTA and no issue slots.
- * status[0] (device int32) is set to 2 if a copy never lands (bounded wait, nothing hangs). */
+ * status[0] (device int32) is set to 2 and the kernel traps if a copy never lands (bounded wait, fatal). */
 int sirgcn_peer_push_tma(const void *src, void *const *dsts, int32_t n_dst, size_t bytes, int32_t n_ctas,
                          int32_t *status, void *stream);
 int sirgcn_peer_barrier(uint32_t *const *pads, int32_t world, int32_t rank, uint32_t epoch, uint64_t timeout_ns,

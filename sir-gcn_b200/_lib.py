@@ -10,6 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIRGCN_LIB") or os.path.join(_HERE, "libsirgcn.so")   # override: kernel-variant A/B runs
 
+ABI_VERSION = 8     # include/sirgcn.h SIRGCN_ABI_VERSION
 F32, BF16, F16 = 0, 1, 2
 ACT_IDENTITY, ACT_RELU, ACT_LEAKY_RELU, ACT_GELU = 0, 1, 2, 3
 
@@ -77,6 +78,10 @@ def lib():
         l.sirgcn_num_tiles.argtypes = [C.c_int32, C.c_int64]
         l.sirgcn_edge_partial_bytes.restype = C.c_size_t
         l.sirgcn_edge_partial_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        l.sirgcn_abi_version.restype = C.c_int
+        if l.sirgcn_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{LIB_PATH} has ABI version {l.sirgcn_abi_version()}, this package needs {ABI_VERSION}: "
+                               "rebuild it (`python -c 'import __graft_entry__ as g; g.build()'`)")
         _lib = l
     return _lib
 

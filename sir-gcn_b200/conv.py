@@ -111,7 +111,12 @@ class SIRConv(nn.Module):
         agg = self._agg_type
         known = classify_activation(self.activation)
         dropping = self.training and self.dropout.p > 0
-        if agg in _SUM_LIKE and known is not None and not inner and not dropping and self._plain():
+        # the fused kernels hold one row in at most 128 16-byte vectors (2048 B: 512 fp32 / 1024 16-bit columns); wider
+        # hidden sizes take the split path below, which has no width limit (the reference accepts any size)
+        dt_ = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else feat.dtype
+        d_hid = self.linear_query.weight.shape[0] if hasattr(self.linear_query, "weight") else 0
+        fits = 0 < d_hid and _pad_cols(d_hid, dt_) * torch.empty((), dtype=dt_).element_size() <= 2048
+        if agg in _SUM_LIKE and known is not None and not inner and not dropping and fits and self._plain():
             # one autograd node for the whole layer (nn.Dropout is the identity here)
             dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else feat.dtype
             w, b, d, _ = self._cat_qk_weights(dt)
@@ -124,7 +129,7 @@ class SIRConv(nn.Module):
                                           bool(recompute))
         q, k = self._project_qk(feat.reshape(-1, feat.shape[-1]))
         e = self._edge_term(g, efeat)
-        if agg in _SUM_LIKE and known is not None and not inner:
+        if agg in _SUM_LIKE and known is not None and not inner and fits:
             a = EdgeAggregate.apply(q, k, e, g, agg, known[0], known[1])
             if type(self.linear_relation) is nn.Linear:
                 return _linear(a, self.linear_relation.weight, self.linear_relation.bias)
@@ -132,7 +137,7 @@ class SIRConv(nn.Module):
         # split path: materialise z in CSR order, run the callable, reduce.  Every op of the edge
         # stage acts per trailing column, so inner dims are folded into the column axis.
         E = g.num_edges()
-        z = GatherAdd.apply(q.reshape(n, -1), k.reshape(n, -1), e, g)
+        z = GatherAdd.apply(q.reshape(n, -1), k.reshape(n, -1), None if e is None else e.reshape(E, -1), g)
         s = self.activation(z.reshape((E,) + inner + (-1,)))
         if agg in _SUM_LIKE:
             a = SegmentReduce.apply(s.reshape(E, -1), g, agg)
@@ -173,11 +178,21 @@ class SIRConvBase(nn.Module):
 
     def forward(self, graph, feat, efeat=None):
         g = as_graph(graph)
-        parts = [GatherAdd.apply(feat, None, None, g), GatherAdd.apply(None, feat, None, g)]
+        if feat.dim() < 2 or feat.shape[0] != g.num_nodes():
+            raise ValueError(f"feat must be [N={g.num_nodes()}, ..., d], got {tuple(feat.shape)}")
+        n, E = g.num_nodes(), g.num_edges()
+        # conv.py:159-166 tolerates [N, ..., d]: the gathers act per trailing column, so inner dims are folded into
+        # the column axis for the kernels and restored before the concatenation along the LAST axis (conv.py:157)
+        shape_e = (E,) + tuple(feat.shape[1:])
+        f2 = feat.reshape(n, -1)
+        parts = [GatherAdd.apply(f2, None, None, g).reshape(shape_e), GatherAdd.apply(None, f2, None, g).reshape(shape_e)]
         if efeat is not None:
-            parts.append(GatherAdd.apply(None, None, efeat, g))
+            if efeat.shape[0] != E:
+                raise ValueError(f"efeat has {efeat.shape[0]} rows but the graph has {E} edges")
+            parts.append(GatherAdd.apply(None, None, efeat.reshape(E, -1), g).reshape(efeat.shape))
         m = self._message_func(torch.cat(parts, dim=-1))
-        return SegmentReduce.apply(m, g, self._agg_type)
+        out = SegmentReduce.apply(m.reshape(E, -1), g, self._agg_type)
+        return out.reshape((n,) + tuple(m.shape[1:]))
 
 
 class SIREConvBase(SIRConvBase):

@@ -27,12 +27,21 @@ inline unsigned blocks_for(int64_t n, int per_block = kThreads) {
     return (unsigned)((n + per_block - 1) / per_block);
 }
 
+// keys outside [0, num_rows) are clamped (nothing downstream may index out of bounds) and reported through *bad:
+// the host raises after its one sync per graph (DGL raises for such a graph too)
 __global__ void iota_copy_kernel(const int32_t *__restrict__ key_in, int32_t *__restrict__ key_out,
-                                 int32_t *__restrict__ val_out, int64_t n) {
+                                 int32_t *__restrict__ val_out, int64_t n, int32_t num_rows, int32_t *bad) {
+    bool any_bad = false;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        key_out[i] = key_in[i];
+        int32_t k = key_in[i];
+        if (k < 0 || k >= num_rows) {
+            any_bad = true;
+            k = k < 0 ? 0 : num_rows - 1;
+        }
+        key_out[i] = k;
         val_out[i] = (int32_t)i;
     }
+    if (any_bad && bad) atomicOr(bad, 1);
 }
 
 // indptr[v] = first position whose key is >= v, from the sorted key array (run boundaries).
@@ -158,14 +167,14 @@ int key_bits(int32_t num_nodes) {
 
 // sort (key, edge id) pairs; write indptr, the "other endpoint" array and (optionally) edge ids
 int build_one(const int32_t *key, const int32_t *other, int64_t E, int32_t N, int32_t *indptr,
-              int32_t *other_sorted, int32_t *eid_sorted, SortScratch &ws, cudaStream_t st) {
+              int32_t *other_sorted, int32_t *eid_sorted, SortScratch &ws, cudaStream_t st, int32_t *bad = nullptr) {
     if (E == 0) {
         empty_indptr_kernel<<<blocks_for(N + 1), kThreads, 0, st>>>(indptr, N);
         SIRGCN_LAUNCHED();
         return SIRGCN_OK;
     }
     const unsigned grid = std::min(blocks_for(E), (unsigned)kNumSMs * 16);
-    iota_copy_kernel<<<grid, kThreads, 0, st>>>(key, ws.keys[0], ws.vals[0], E);
+    iota_copy_kernel<<<grid, kThreads, 0, st>>>(key, ws.keys[0], ws.vals[0], E, N, bad);
     SIRGCN_LAUNCHED();
     cub::DoubleBuffer<int32_t> k(ws.keys[0], ws.keys[1]), v(ws.vals[0], ws.vals[1]);
     size_t bytes = ws.cub_bytes;
@@ -365,9 +374,12 @@ int sirgcn_csr_build(const int32_t *src, const int32_t *dst, int64_t num_edges, 
         ws.cub_tmp = base + 4 * arr;
         ws.cub_bytes = workspace_bytes - 4 * arr;
     }
-    int rc = build_one(dst, src, num_edges, num_nodes, indptr_in, col_src, eid_in, ws, st);
+    SIRGCN_CHECK_ARG(num_edges == 0 || num_nodes > 0, "edges on a graph without nodes");
+    int32_t *bad = counts ? counts + 4 : nullptr;        // every id is a key of one of the two sorts: both are checked
+    if (bad) SIRGCN_CUDA(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
+    int rc = build_one(dst, src, num_edges, num_nodes, indptr_in, col_src, eid_in, ws, st, bad);
     if (rc) return rc;
-    rc = build_one(src, dst, num_edges, num_nodes, indptr_out, row_dst, eid_out, ws, st);
+    rc = build_one(src, dst, num_edges, num_nodes, indptr_out, row_dst, eid_out, ws, st, bad);
     if (rc) return rc;
     if ((in_norm || out_norm || inv_in_deg) && num_nodes > 0) {
         norms_kernel<<<std::min(blocks_for(num_nodes), (unsigned)kNumSMs * 16), kThreads, 0, st>>>(

@@ -27,7 +27,8 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 
 // pads[r] = rank r's flag pad (uint32 [kPadSlots]); slot `rank` of every peer's pad <- epoch, then wait until
 // every slot of the own pad has reached the epoch.  Epochs only grow (wrap-safe signed compare).
-// status[0] is set to 1 if the spin gave up (a peer never arrived): the host checks it, nothing hangs.
+// If the spin gives up (a peer never arrived) status[0] is set to 1 and the kernel TRAPS: the context is dead, every
+// later CUDA call of this process fails loudly, and no kernel ever runs on tables that were not gathered or pushed.
 __global__ void peer_barrier_kernel(uint32_t *const *pads, int world, int rank, uint32_t epoch,
                                     unsigned long long timeout_ns, int *status) {
     const int t = threadIdx.x;
@@ -39,7 +40,8 @@ __global__ void peer_barrier_kernel(uint32_t *const *pads, int world, int rank, 
         while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
             if (globaltimer_ns() - t0 > timeout_ns) {
                 atomicExch(status, 1);
-                break;
+                __threadfence_system();
+                __trap();
             }
             __nanosleep(200);
         }
@@ -128,9 +130,10 @@ __global__ void __launch_bounds__(32) peer_push_tma_kernel(const char *__restric
         }
         unsigned spins = 0;
         while (!mbar_try_wait(smem_addr(&full[s]), parity)) {
-            if (++spins > (1u << 26)) {                     // a copy that never lands: report, do not hang
+            if (++spins > (1u << 26)) {                     // a copy that never lands: report and kill the context
                 atomicExch(status, 2);
-                return;
+                __threadfence_system();
+                __trap();
             }
         }
         const uint32_t from = smem_addr(ring + (size_t)s * kTmaChunk), nb = chunk_bytes(c);

@@ -128,7 +128,7 @@ class Graph:
         sched_in, sched_out = _sched_alloc(E, thr, dev), _sched_alloc(E, thr, dev)
         s_in = _lib.Schedule(*[_lib.ptr(t).value for t in sched_in])
         s_out = _lib.Schedule(*[_lib.ptr(t).value for t in sched_out])
-        counts = torch.zeros(4, dtype=torch.int32, device=dev)
+        counts = torch.zeros(5, dtype=torch.int32, device=dev)
         L = _lib.lib()
         ws_bytes = L.sirgcn_csr_build_workspace_bytes(E, N)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -141,8 +141,10 @@ class Graph:
                 C.c_int32(thr), C.byref(s_in), C.byref(s_out), _lib.ptr(counts),
                 _lib.ptr(ws), C.c_size_t(ws_bytes), _lib.stream_ptr(dev))
         _lib.check(rc, "sirgcn_csr_build")
-        c = counts.tolist()  # the one host sync per graph: sizes of the long-row schedule
+        c = counts.tolist()  # the one host sync per graph: sizes of the long-row schedule (+ the id range flag)
         del ws
+        if c[4]:
+            raise ValueError(f"node ids out of range [0, {N}) in src/dst")
         self.csr = CompressedRows(indptr_in, col_src, eid_in, thr, sched_in, c[0:2])
         self.csc = CompressedRows(indptr_out, row_dst, eid_out, thr, sched_out, c[2:4])
         self.src, self.dst = (src, dst) if keep_coo else (None, None)
@@ -237,6 +239,8 @@ class Graph:
 
     def csc_pos(self):
         """CSR position of the edge stored at every CSC position (int32 [E])"""
+        if self.csr.eid is None:
+            raise RuntimeError("graph was built with need_eid=False")
         t = self._lazy.get("csc_pos")
         if t is None:
             inv = torch.empty(self.num_edges_, dtype=torch.int32, device=self.device)

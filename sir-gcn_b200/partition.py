@@ -380,13 +380,11 @@ class RowPartition:
 
 
 def auto_transport(world):
-    """From 4 GPUs up: copy-engine pushes into IPC-mapped peer tables.  Alone they move a table more slowly than NCCL
-    (537 vs 665 GB/s per rank at 8 GPUs, profiles/r01_peer_bw_n8.json) but they take no SM, and in the step every
-    transfer but one runs under an edge walk: NCCL's kernels slow those walks by 30-45 % (forward 17.6 vs 12.1 ms,
-    dQ 18.9 vs 13.9 ms at 8 GPUs).  At 2 GPUs the transfers are small, NCCL is kept: its gathered tables come from
-    the caching allocator, which matters when the 2 B-edge graph leaves ~35 GiB free per GPU."""
-    return "push" if world >= 4 else "collective"
-
+    """NCCL all-gathers at every world size: the best schedule MEASURED inside the step (8 GPUs, 2 B-edge graph:
+    160 ms with NCCL against 207 ms with copy-engine pushes — a push that takes 21 ms alone takes ~48 ms under an
+    HBM-saturating walk, SCALE_r01.json).  The peer-memory transports stay selectable (`transport=` /
+    SIRGCN_TRANSPORT); a default only changes on an in-step A/B committed under profiles/."""
+    return "collective"
 
 
 # bench.py sets this to a list to collect (label, CUDA event) marks on the compute stream (phase breakdown)

@@ -31,7 +31,10 @@ import torch.distributed as dist
 
 from . import _lib
 
-_BARRIER_TIMEOUT_NS = 20_000_000_000      # a peer that has not arrived after 20 s is reported, nothing hangs
+# a peer that has not arrived after this long is fatal: the barrier kernel records status 1 and traps, so nothing ever
+# computes on tables that were not gathered (a rank stalled by a checkpoint save or an eval needs a longer limit:
+# SIRGCN_BARRIER_TIMEOUT_S)
+_BARRIER_TIMEOUT_NS = int(float(os.environ.get("SIRGCN_BARRIER_TIMEOUT_S", "120")) * 1e9)
 
 
 class _RawDeviceBuffer:
@@ -50,6 +53,7 @@ class PeerSlice:
         self.base, self.local, self.peer_ptr = base, local, peer_ptr
         self.row_bytes = ld * local.element_size()
         self.waited_at = -1         # index of the newest barrier issued when the last pull of this slice was waited for
+        self.gathered = False       # peers have pulled (or may still be pulling) the current contents
         self.pending = []           # PullHandles of gathers that have not been waited for yet
 
 
@@ -237,8 +241,13 @@ class PeerPool:
         """call before the producer overwrites sl.local: fences the peers' pulls of its previous contents"""
         for h in list(sl.pending):
             h.wait()
-        if sl.waited_at >= 0 and self.joined <= sl.waited_at:
+        # Every rank must issue the SAME number of barriers (the flag epochs are per-rank counters), so the decision
+        # may only depend on what the SPMD program did explicitly: `gathered` is set by gather(), never from a
+        # finalizer.  (waited_at / joined are written by wait(), which release() may call from _Lease.__del__ at a
+        # GC-dependent moment — they are bookkeeping only.)
+        if sl.gathered:
             self.barrier(blocking=True)
+        sl.gathered = False
         sl.waited_at = -1
 
     # ---- the all-gather -----------------------------------------------------------------------------------------
@@ -268,6 +277,7 @@ class PeerPool:
         full[self.rank * sl.rows + lo:self.rank * sl.rows + hi].copy_(sl.local[lo:hi])
         h = PullHandle(self, sl, events, index)
         sl.pending.append(h)
+        sl.gathered = True
         return h
 
     # ---- push variant: the gathered tables are the peer-mapped objects ------------------------------------------
@@ -296,18 +306,18 @@ class PeerPool:
         been waited for) -> rows rank*rows + lo.. of EVERY rank's table.  mode "ce": one copy-engine write per peer;
         "sm": one fan-out kernel of a few CTAs (sirgcn_peer_push); "tma": the same with TMA bulk copies issued by one
         thread per CTA (sirgcn_peer_push_tma).  Two barriers frame the transfer, neither blocks
-        the current stream: "every rank is done reading the table's previous contents" (skipped when a barrier has
-        been issued since the table was released) and "every rank's rows have landed".  Returns a PushHandle."""
+        the current stream: "every rank is done reading the table's previous contents" and "every rank's rows have
+        landed".  Returns a PushHandle."""
         hi = pf.rows if hi is None else hi
         cur = torch.cuda.current_stream(self.device)
         mine = self.rank * pf.rows
         if self.world == 1:
             pf.local[lo:hi].copy_(src[lo:hi])
             return PushHandle(self, None, self.barriers)
-        if self.barriers > pf.released_at and self._last_done[0] > pf.released_at:
-            free_ev = self._last_done[1]
-        else:
-            _, free_ev = self.barrier(blocking=False)
+        # "every rank is done reading the table's previous contents": always a barrier of its own.  Skipping it when
+        # one has been issued since release_full() would make the barrier COUNT depend on when the lease was released
+        # — possibly from a finalizer, at a different moment on every rank — and skew the per-rank flag epochs.
+        _, free_ev = self.barrier(blocking=False)
         ready = torch.cuda.Event()
         ready.record(cur)                                   # the producer of src[lo:hi]
         nbytes, off = (hi - lo) * pf.row_bytes, (mine + lo) * pf.row_bytes
