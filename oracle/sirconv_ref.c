@@ -52,7 +52,9 @@ static int coefficients(int64_t E, int32_t N, const int64_t *src, const int64_t 
     }
     for (int64_t e = 0; e < E; ++e) {
         const double di = in_deg[dst[e]] < 1 ? 1 : in_deg[dst[e]], dq = out_deg[src[e]] < 1 ? 1 : out_deg[src[e]];
-        coef[e] = agg == AGG_SYM ? (1.0 / sqrt(dq)) * (1.0 / sqrt(di)) : agg == AGG_MEAN ? 1.0 / di : 1.0;
+        /* the reference takes the norms in fp32 (conv.py:51-52 `.float()`, then torch.pow(., -0.5)): fp32 values here too
+         * (IEEE 1/sqrt; torch's pow may differ from it in the last fp32 bit) */
+        coef[e] = agg == AGG_SYM ? (double)(1.0f / sqrtf((float)dq)) * (double)(1.0f / sqrtf((float)di)) : agg == AGG_MEAN ? 1.0 / di : 1.0;
     }
     free(in_deg);
     free(out_deg);

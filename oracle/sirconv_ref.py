@@ -5,11 +5,15 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 (``sir-gcn_b200/``, ``models/``) never does: it fails loudly if the CUDA library
 is missing.
 
-PARITY UNPINNED against DGL: the reference layer (/root/reference/models/conv.py)
-imports ``dgl`` at module import time (conv.py:3-4); DGL 2.1.0 (requirements.txt:1)
-is not installed here and the reference ships no tests / golden vectors.  This file
-restates the layer's arithmetic op-for-op with the ATen operations DGL lowers
-``update_all(UDF message, builtin reduce)`` to:
+PINNED ON THE REFERENCE'S OWN CODE (not on DGL's): the reference layer (/root/reference/models/conv.py) imports
+``dgl`` at module import time (conv.py:3-4); DGL 2.1.0 (requirements.txt:1) is not installable here and the
+reference ships no tests / golden vectors.  tests/golden/make_golden.py therefore executes the UNMODIFIED conv.py
+with its eight DGL symbols served by the stand-in under tests/fake_dgl/ and commits the results
+(tests/golden/sirconv_golden.pt: 4 classes x 5 aggregators, fp64); tests/test_oracle_pins.py requires this
+restatement to reproduce them — outputs and all gradients — to 1e-12, and repeats the comparison live on fresh
+cases wherever /root/reference exists.  What remains unpinned is DGL's own arithmetic behind those eight symbols
+(documented semantics only).  This file restates the layer's arithmetic op-for-op with the ATen operations DGL
+lowers ``update_all(UDF message, builtin reduce)`` to:
 
 * edge-UDF gathers  -> ``index_select``          (conv.py:45  edges.src[...]/edges.dst[...])
 * message           -> elementwise add/σ/mul      (conv.py:43-47, 109-113)
@@ -18,7 +22,7 @@ restates the layer's arithmetic op-for-op with the ATen operations DGL lowers
 * ``fn.max``        -> ``scatter_reduce_('amax', include_self=False)``, empty rows = 0
 * degrees           -> ``bincount`` + ``clamp(min=1)``   (conv.py:51-52)
 
-What pins it instead (tests/test_oracle_pins.py): fp64 ``gradcheck``, the
+Further, independent pins (tests/test_oracle_pins.py): fp64 ``gradcheck``, the
 hetero-edge-count exact-count identity (synthetic-datasets/hetero-edge-count/data.py:21),
 the dictionary-lookup isolated-destination identity (dictionary-lookup/data.py:27-31),
 algebraic identities (sym on a regular graph, mean = sum/deg, edge permutation
@@ -71,14 +75,16 @@ def _reduce(graph: RefGraph, msg: torch.Tensor, how: str) -> torch.Tensor:
 
 
 def _norms(graph: RefGraph, agg: str, like: torch.Tensor):
-    """conv.py:51-57 — clamped degrees, ^-1/2 only for 'sym'."""
+    """conv.py:51-57 — clamped degrees, ^-1/2 only for 'sym'.  The reference computes them with `.float()`
+    (conv.py:51-52) whatever the dtype of the features: they are fp32 values that the per-edge product then promotes
+    (found by running the unmodified layer in fp64 against this restatement, tests/test_oracle_pins.py)."""
     shape = (graph.n,) + (1,) * (like.dim() - 1)
     if agg == "sym":
-        i = graph.in_degrees().to(like.dtype).clamp(min=1).pow(-0.5)
-        o = graph.out_degrees().to(like.dtype).clamp(min=1).pow(-0.5)
+        i = torch.pow(graph.in_degrees().float().clamp(min=1), -0.5)
+        o = torch.pow(graph.out_degrees().float().clamp(min=1), -0.5)
     else:
-        i = like.new_ones(graph.n)
-        o = like.new_ones(graph.n)
+        i = torch.ones(graph.n)
+        o = torch.ones(graph.n)
     return i.reshape(shape), o.reshape(shape)
 
 

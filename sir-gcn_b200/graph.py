@@ -291,7 +291,10 @@ def as_graph(graph) -> Graph:
             cached = None
         if cached is not None:
             return cached
-        src, dst = graph.edges(form="uv", order="eid")
+        src, dst = graph.edges(form="uv", order="eid")     # int64 by default in DGL; Graph narrows to int32
+        if not src.is_cuda:
+            raise RuntimeError("the DGLGraph lives on the host: move it to the GPU first (`graph.to(device)`, as the "
+                               "reference scripts do) — the SIR-GCN kernels need CUDA tensors and have no CPU fallback")
         g = Graph(src, dst, graph.num_nodes())
         try:
             _dgl_cache[graph] = g

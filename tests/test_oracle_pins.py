@@ -1,8 +1,11 @@
 """Pins of the CPU oracle (oracle/sirconv_ref.py, oracle/csr_ref.c).
 
-The reference has no tests and cannot be imported without DGL ("parity unpinned"),
-so the oracle is pinned by known-answer identities derived from the reference's own data generators
-and by algebraic properties of the layer, plus frozen golden vectors.
+The reference has no tests of its own and imports DGL (not installable here).  The oracle is pinned on the
+reference's OWN CODE: tests/golden/sirconv_golden.pt was produced by executing the unmodified
+/root/reference/models/conv.py with its DGL imports served by the stand-in under tests/fake_dgl/
+(tests/golden/make_golden.py), and the oracle must reproduce it to 1e-12; in this container the same comparison
+also runs live on fresh random cases.  Known-answer identities derived from the reference's own data generators and
+algebraic properties of the layer are kept as independent pins.
 """
 import os
 
@@ -186,24 +189,76 @@ def test_min_and_unknown_aggregators():
 
 
 # ---- frozen vectors ----------------------------------------------------------------------------
-def test_oracle_reproduces_golden():
-    from tests.golden.make_golden import ACTS
+ORACLE_NS = {"SIRConv": RefSIRConv, "SIREConv": RefSIREConv, "SIRConvBase": RefSIRConvBase,
+             "SIREConvBase": RefSIREConvBase}
+
+
+def _check_oracle_against(c, tol=1e-12):
+    """the restated oracle, in fp64, against one case produced by the reference's own code"""
+    from tests.golden.make_golden import build_layer
+    m = c["meta"]
+    layer = build_layer(ORACLE_NS, m)
+    layer.load_state_dict(c["state"])
+    layer = layer.double()
+    feat = c["feat"].double().requires_grad_(True)
+    has_e = c["efeat"] is not None
+    ef = c["efeat"].double().requires_grad_(True) if has_e else None
+    out = layer(RefGraph(c["src"], c["dst"], m["n"]), feat, ef) if has_e else layer(RefGraph(c["src"], c["dst"], m["n"]), feat)
+    torch.testing.assert_close(out, c["out"], rtol=tol, atol=tol)
+    params = list(layer.named_parameters())
+    grads = torch.autograd.grad(out, [feat] + ([ef] if has_e else []) + [p for _, p in params], c["gout"].double(),
+                                allow_unused=True)
+    torch.testing.assert_close(grads[0], c["dfeat"], rtol=tol, atol=tol)
+    if has_e:
+        torch.testing.assert_close(grads[1], c["defeat"], rtol=tol, atol=tol)
+    for (name, p), gr in zip(params, grads[(2 if has_e else 1):]):
+        torch.testing.assert_close(torch.zeros_like(p) if gr is None else gr, c["dparams"][name], rtol=tol, atol=tol)
+
+
+def test_oracle_reproduces_reference_goldens():
+    """THE PIN: every committed case was produced by executing the unmodified /root/reference/models/conv.py
+    (tests/golden/make_golden.py, DGL served by tests/fake_dgl); the oracle must agree to 1e-12 in fp64 — outputs,
+    input / edge-feature gradients and every weight gradient, 4 classes x 5 aggregators."""
     cases = torch.load(GOLDEN)
-    assert len(cases) >= 16
+    assert len(cases) >= 35
+    seen = {(c["meta"]["cls"], c["meta"]["agg"]) for c in cases}
+    assert seen >= {(k, a) for k in ORACLE_NS for a in ("sum", "mean", "sym", "max", "min")}
     for c in cases:
-        m = c["meta"]
-        if m["edge_dim"]:
-            layer = RefSIREConv(m["d_in"], m["edge_dim"], m["d"], m["d_out"], ACTS[m["act"]](), agg_type=m["agg"])
-        else:
-            layer = RefSIRConv(m["d_in"], m["d"], m["d_out"], ACTS[m["act"]](), agg_type=m["agg"])
-        layer.load_state_dict(c["state"])
-        feat = c["feat"].clone().requires_grad_(True)
-        out = layer(RefGraph(c["src"], c["dst"], m["n"]), feat, c["efeat"])
-        torch.testing.assert_close(out, c["out"], rtol=1e-6, atol=1e-6)
-        (dfeat,) = torch.autograd.grad(out, feat, c["gout"])
-        torch.testing.assert_close(dfeat, c["dfeat"], rtol=1e-6, atol=1e-6)
-        for x, y in zip(csr_csc_ref(c["src"], c["dst"], m["n"])[:6], c["csr"][:6]):
+        _check_oracle_against(c)
+        for x, y in zip(csr_csc_ref(c["src"], c["dst"], c["meta"]["n"])[:6], c["csr"][:6]):
             assert torch.equal(x, y)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/conv.py"), reason="the reference tree is not on this box")
+def test_oracle_matches_reference_executed_live():
+    """fresh random cases (other seeds and shapes than the committed fixture) through the reference's own code, live"""
+    from tests.golden.make_golden import load_reference, make_case
+    ref, dgl = load_reference()
+    seed = 900
+    for cls, edge_dim in (("SIRConv", 0), ("SIREConv", 5), ("SIRConvBase", 0), ("SIREConvBase", 3)):
+        for agg in ("sum", "mean", "sym", "max", "min"):
+            for act in (("relu", "gelu") if cls.endswith("Conv") else ("",)):
+                _check_oracle_against(make_case(ref, dgl, seed, cls, 31, 140, 7, 9, 6, act, agg, edge_dim=edge_dim))
+                seed += 1
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/conv.py"), reason="the reference tree is not on this box")
+def test_reference_dropout_order_is_key_query_edge():
+    """conv.py:60-61,128 draw the dropout masks in the order K, Q, E — the oracle must consume the RNG identically"""
+    from tests.golden.make_golden import load_reference
+    ref, dgl = load_reference()
+    g = torch.Generator().manual_seed(5)
+    n, e = 20, 70
+    src, dst = torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)
+    x, ef = torch.randn(n, 6, generator=g), torch.randn(e, 3, generator=g)
+    a = ref.SIREConv(6, 3, 8, 4, nn.ReLU(), dropout=0.4, agg_type="sym")
+    b = RefSIREConv(6, 3, 8, 4, nn.ReLU(), dropout=0.4, agg_type="sym")
+    b.load_state_dict(a.state_dict())
+    torch.manual_seed(11)
+    out_a = a(dgl.graph((src, dst), num_nodes=n), x, ef)
+    torch.manual_seed(11)
+    out_b = b(RefGraph(src, dst, n), x, ef)
+    torch.testing.assert_close(out_a, out_b, rtol=1e-6, atol=1e-6)
 
 
 # ---- two independent restatements agree: torch ops + autograd  vs  plain C loops + hand-written derivative -----------
@@ -243,6 +298,9 @@ def test_c_restatement_matches_torch_oracle(agg, act):
     da = torch.randn(n, d, generator=g, dtype=torch.float64)
     dq_t, dk_t, de_t = torch.autograd.grad(a_t, (q, k, pe), da)
     a_c, dq_c, dk_c, de_c = edge_stage_c(src, dst, n, q, k, pe, act, 0.2, agg, da)
+    # 'sym': both take the norms in fp32 as the reference does, but torch.pow(x, -0.5) and IEEE 1/sqrt(x) may differ in
+    # the last fp32 bit (6e-8) — a platform detail, not layer semantics
+    tol = 1e-6 if agg == "sym" else 1e-12
     for got, want in ((a_c, a_t), (dq_c, dq_t), (dk_c, dk_t), (de_c, de_t)):
-        torch.testing.assert_close(got, want.detach(), rtol=1e-12, atol=1e-12)
+        torch.testing.assert_close(got, want.detach(), rtol=tol, atol=tol)
     assert torch.equal(a_c[11], torch.zeros(d, dtype=torch.float64))
