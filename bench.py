@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — SIR-GCN conv fwd+bwd throughput (Gedges/s) and fraction of the HBM roofline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload P|A] [--scale S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload P|A|Z|C] [--dtype f32|bf16] [--scale S]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...        # the reference's CPU path (oracle port) on host cores
 
@@ -48,7 +48,14 @@ WORKLOADS = {
               act="relu", max_deg=None, desc="power-law 50M nodes / 2B edges, d=128, 2 layers (BASELINE configs[4])"),
     "A": dict(nodes=169_343, edges=1_166_243, d_in=128, d=256, layers=3, dtype="f32", agg="sum",
               act="leaky", max_deg=13_000, desc="ogbn-arxiv-shaped 169,343 nodes / 1.17M edges, 128->256, 3 layers (configs[2])"),
+    # batched small graphs: a NEW batch (graph conversion included) every step, data-parallel over the GPUs
+    "Z": dict(nodes=128 * 23, edges=128 * 50, d_in=64, d=64, layers=4, dtype="f32", agg="sum", act="leaky",
+              max_deg=None, edge_types=4,
+              desc="ZINC-shaped batch: 128 molecular graphs x 23 nodes / 50 edges, bond-type edge term, d=64, 4 layers (configs[1])"),
+    "C": dict(nodes=None, edges=None, d_in=5, d=128, layers=4, dtype="f32", agg="sum", act="leaky", max_deg=None,
+              desc="CIFAR10-super-pixel-shaped batch: 128 kNN graphs (k=8, 85..150 nodes), 5->128, 4 layers (configs[3])"),
 }
+BATCHED = ("Z", "C")
 DTYPES = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}
 
 
@@ -130,31 +137,68 @@ def cpu_sample_shape(w, target_edges):
     return max(64, w["nodes"] // f), max(64, w["edges"] // f), f
 
 
-def build_cpu_case(w, target_edges):
-    from oracle.sirconv_ref import RefGraph, RefSIRConv
+def small_batch(name, w, seed):
+    """one synthetic input of a small workload on the host: dict(src, dst int32, n, x fp32 [n, d_in], etype int64 | None)"""
     from sirgcn_b200 import synth
-    n, e, f = cpu_sample_shape(w, target_edges)
-    src, dst, n = synth.powerlaw(n, e, alpha=2.3, max_deg=w["max_deg"], seed=0, device="cpu", index_dtype=torch.int64)
-    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(1000 + seed)
+    if name == "Z":
+        src, dst, n, _, bond = synth.zinc_like(num_graphs=128, seed=seed)
+        return dict(src=src.int(), dst=dst.int(), n=n, x=torch.randn(n, w["d_in"], generator=g), etype=bond)
+    if name == "C":
+        src, dst, n, pos, _ = synth.cifar_like(num_graphs=128, seed=seed)
+        return dict(src=src.int(), dst=dst.int(), n=n, x=torch.cat([torch.rand(n, 3, generator=g), pos], 1), etype=None)
+    src, dst, n = synth.arxiv_like(seed=seed)
+    return dict(src=src.int(), dst=dst.int(), n=n, x=torch.randn(n, w["d_in"], generator=g), etype=None)
+
+
+def small_layers(w, sir, sire, edge_types=None):
+    """the L conv layers of a small workload from the given classes (CUDA package or oracle)"""
     dims = [w["d_in"]] + [w["d"]] * w["layers"]
-    layers = [RefSIRConv(dims[i], w["d"], w["d"], make_act(w["act"]), agg_type=w["agg"]) for i in range(w["layers"])]
-    x = torch.randn(n, w["d_in"])
+    layers = []
+    for i in range(w["layers"]):
+        if edge_types:
+            c = sire(dims[i], edge_types, w["d"], w["d"], make_act(w["act"]), agg_type=w["agg"])
+            c.linear_edge = nn.Embedding(edge_types, w["d"])        # benchmark-datasets/zinc/model.py:12-15
+        else:
+            c = sir(dims[i], w["d"], w["d"], make_act(w["act"]), agg_type=w["agg"])
+        layers.append(c)
+    return nn.ModuleList(layers)
+
+
+def build_cpu_case(args, w):
+    """(step function, edges x layers per step, description of the sample) of the CPU arm: the oracle port"""
+    from oracle.sirconv_ref import RefGraph, RefSIRConv, RefSIREConv
+    from sirgcn_b200 import synth
+    torch.manual_seed(0)
+    if args.workload == "P":
+        n, e, f = cpu_sample_shape(w, args.cpu_edges)
+        src, dst, n = synth.powerlaw(n, e, alpha=2.3, max_deg=w["max_deg"], seed=0, device="cpu", index_dtype=torch.int64)
+        x, etype = torch.randn(n, w["d_in"]), None
+        sample = (f"1/{f} sample of the workload with the same degree law: {n:,} nodes / {e:,} edges, fp32, "
+                  f"{w['layers']} layers fwd+bwd, oracle/sirconv_ref.py (index_select / index_add_, the ops DGL lowers to)")
+        shape = {"nodes": n, "edges": e, "fraction": f"1/{f}"}
+    else:
+        b = small_batch(args.workload, w, 0)
+        src, dst, n, x, etype = b["src"].long(), b["dst"].long(), b["n"], b["x"], b["etype"]
+        e = int(src.numel())
+        sample = (f"the whole workload: {n:,} nodes / {e:,} edges, fp32, {w['layers']} layers fwd+bwd, "
+                  f"oracle/sirconv_ref.py (index_select / index_add_, the ops DGL lowers to)")
+        shape = {"nodes": n, "edges": e, "fraction": "1/1"}
+    layers = small_layers(w, RefSIRConv, RefSIREConv, w.get("edge_types"))
     gout = torch.randn(n, w["d"])
     g = RefGraph(src, dst, n)
 
     def step():
         h = x.clone().requires_grad_(True)
-        for p in (p for l in layers for p in l.parameters()):
+        for p in layers.parameters():
             p.grad = None
         out = h
         for l in layers:
-            out = l(g, out)
+            out = l(g, out, etype) if etype is not None else l(g, out)
         out.backward(gout)
         return float(out.detach().sum())
 
-    sample = (f"1/{f} sample of the workload with the same degree law: {n:,} nodes / {e:,} edges, fp32, "
-              f"{w['layers']} layers fwd+bwd, oracle/sirconv_ref.py (index_select / index_add_, the ops DGL lowers to)")
-    return step, e * w["layers"], sample
+    return step, e * w["layers"], sample, shape
 
 
 def time_cpu(step, steps, warmup):
@@ -172,14 +216,18 @@ def run_reference(args, w):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step, edges_per_step, sample = build_cpu_case(w, args.cpu_edges)
+    step, edges_per_step, sample, shape = build_cpu_case(args, w)
     t = time_cpu(step, args.steps, args.warmup)
     value = edges_per_step / t / 1e9
+    cfg = workload_config(args, w)
+    # the CPU arm times a BOUNDED SAMPLE of the workload named above: say so in the config itself
+    cfg["reference_sample"] = dict(shape, dtype="f32", note="what this line actually timed; `nodes`/`edges` above name "
+                                   "the workload the sample is drawn from")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, w),
+        "scaling": "weak" if args.workload in BATCHED else "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -194,6 +242,19 @@ def emit(line):
 
 
 def workload_config(args, w):
+    if args.workload != "P":
+        c_nodes = w["nodes"] if w["nodes"] else "128 graphs x U{85..150} (~15.0 k per batch)"
+        c_edges = w["edges"] if w["edges"] else "8 x nodes (~120 k per batch)"
+        per_step = ("a NEW batch every step: COO -> CSR/CSC conversion (Graph) and DropEdge(0) per layer are inside the "
+                    "timed region" if args.workload in BATCHED else "static graph, converted once")
+        return {"workload": f"{args.workload}: {w['desc']}", "nodes": c_nodes, "edges": c_edges, "d_in": w["d_in"],
+                "d_hidden": w["d"], "layers": w["layers"], "agg": w["agg"], "activation": w["act"],
+                "table_dtype": w["dtype"], "per_step": per_step,
+                "partition": "single GPU" if args.gpus == 1 else
+                (f"data parallel over {args.gpus} GPUs: one batch per GPU per step, replicated weights, ONE flat NCCL "
+                 f"all-reduce of the weight gradients per step" if args.workload in BATCHED else
+                 f"{args.gpus} independent replicas (the graph fits one GPU: replicas only, no collective)"),
+                "l2": "L2 flushed (256 MiB write) between timed steps"}
     n, e = scaled_shape(args, w)
     return {"workload": f"{args.workload}: {w['desc']}" + ("" if args.scale == 1 else f" at scale {args.scale:g}"),
             "nodes": n, "edges": e, "d_in": w["d_in"], "d_hidden": w["d"], "layers": w["layers"],
@@ -228,6 +289,244 @@ def scaled_shape(args, w):
 
 
 # ------------------------------------------------------------------------------------------------
+# parity gate of the partitioned path (N > 1), run before anything is timed
+# ------------------------------------------------------------------------------------------------
+def partition_parity_check(args, w, layers, dev, rank, world):
+    """The L-layer stack on a ~1 M-edge hashed power-law graph through THE transport and schedule that will be timed,
+    against (a) the single-rank kernels on the whole graph (every rank) and (b) the fp64 CPU oracle (rank 0): output
+    rows, input-gradient rows and every weight gradient.  Returns the dict that goes into the JSON line; the caller
+    exits non-zero above 2e-2 (the bf16 tolerance of north_star)."""
+    import torch.distributed as dist
+    from sirgcn_b200 import Graph, partition, synth
+    dtype = DTYPES[w["dtype"]]
+    n, e, d = 100_000, 1_000_000, w["d"]
+    src, dst, _ = synth.powerlaw_hashed(n, e, alpha=2.3, max_deg=None, seed=3, device=dev)
+    whole = Graph(src, dst, n, need_eid=False)
+    part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, alpha=2.3, max_deg=None, seed=3, device=dev,
+                                                     transport=args.transport)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)                                   # the same features on every rank
+    x = torch.randn((n, w["d_in"]), generator=gen, device=dev).to(dtype)
+    gout = torch.randn((n, d), generator=gen, device=dev).to(dtype)
+    params = list(layers.parameters())
+
+    def grads_of(fn, xin, g):
+        for p in params:
+            p.grad = None
+        xin = xin.detach().clone().requires_grad_(True)
+        out = fn(xin)
+        out.backward(g)
+        return out.detach(), xin.grad, [p.grad.detach().clone() for p in params]
+
+    def single(h):
+        for layer in layers:
+            h = layer(whole, h)
+        return h
+
+    out1, dx1, dw1 = grads_of(single, x, gout)
+    lo, hi = part.lo, part.hi
+    feat_full = None if args.no_input_gather else part.all_gather_rows(x[lo:hi])
+    outp, dxp, dwp = grads_of(lambda h: partition.partitioned_sirconv_stack(
+        list(layers), part, h, chunks=args.chunks, gather=args.gather, bwd_chunks=args.bwd_chunks,
+        feat_full=feat_full), x[lo:hi], gout[lo:hi])
+
+    def rel(a, b):
+        a, b = a.double(), b.double()
+        return float((a - b).abs().max() / b.abs().max().clamp(min=1e-20)) if b.numel() else 0.0
+
+    errs = {"out": rel(outp, out1[lo:hi]), "dX": rel(dxp, dx1[lo:hi]),
+            "dW": max(rel(a, b) for a, b in zip(dwp, dw1))}
+    res = {"graph": f"hashed power-law {n:,} nodes / {e:,} edges, {w['layers']} layers, {w['dtype']}",
+           "transport": part.transport().kind, "vs_single_rank_kernels": errs}
+    if rank == 0:
+        from oracle.sirconv_ref import RefGraph, RefSIRConv
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref = small_layers(w, RefSIRConv, None).double()
+        ref.load_state_dict({k: v.detach().cpu().double() for k, v in layers.state_dict().items()})
+        xr = x.detach().cpu().double().requires_grad_(True)
+        h = xr
+        rg = RefGraph(src.cpu().long(), dst.cpu().long(), n)
+        for l in ref:
+            h = l(rg, h)
+        gr = torch.autograd.grad(h, [xr] + list(ref.parameters()), gout.cpu().double())
+        res["vs_fp64_oracle"] = {"out": rel(outp.cpu(), h.detach()[lo:hi]), "dX": rel(dxp.cpu(), gr[0][lo:hi]),
+                                 "dW": max(rel(a.cpu(), b) for a, b in zip(dwp, gr[1:]))}
+        del ref, xr, h, gr, rg
+    worst = torch.tensor([max(errs.values())], device=dev, dtype=torch.float64)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    res["max_rel_err"] = max(float(worst), max(res.get("vs_fp64_oracle", {"x": 0.0}).values()))
+    res["tolerance"] = 2e-2 if dtype != torch.float32 else 1e-5
+    for p in params:
+        p.grad = None
+    del whole, part, x, gout, out1, dx1, dw1, outp, dxp, dwp
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# small workloads: Z / C (a new batch of small graphs every step, data parallel) and A (one static graph)
+# ------------------------------------------------------------------------------------------------
+def run_small(args, w):
+    import torch.distributed as dist
+    import sirgcn_b200  # noqa: F401  (fails loudly if libsirgcn.so is missing: no CPU fallback)
+    from sirgcn_b200 import DropEdge, Graph, SIRConv, SIREConv, _lib, function
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback); use --impl reference")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    name, batched = args.workload, args.workload in BATCHED
+    dp = batched and world > 1
+    dtype = DTYPES[w["dtype"]]
+    L, d = w["layers"], w["d"]
+    torch.manual_seed(0)
+    layers = small_layers(w, SIRConv, SIREConv, w.get("edge_types")).to(dev)
+    if dtype != torch.float32:
+        layers = layers.to(dtype)
+    if world > 1:
+        for p in layers.parameters():
+            dist.broadcast(p.data, 0)
+    params = list(layers.parameters())
+    drop = DropEdge(0.0)          # the reference calls DropEdge per layer per step even at p = 0 (zinc/model.py:50)
+
+    # a pool of host batches (pinned): a different one per step and per rank for Z / C, the one graph for A
+    pool = [small_batch(name, w, 17 * rank + i) for i in range(4 if batched else 1)]
+    for b in pool:
+        b["x"] = b["x"].to(dtype)
+        b["gout"] = torch.randn(b["n"], d, generator=torch.Generator().manual_seed(5)).to(dtype)
+        for k in ("src", "dst", "x", "gout", "etype"):
+            if b[k] is not None:
+                b[k] = b[k].pin_memory()
+    edges_per_step = sum(int(b["src"].numel()) for b in pool) / len(pool)
+    nodes_per_step = sum(b["n"] for b in pool) / len(pool)
+
+    def to_dev(b):
+        return {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in b.items()}
+
+    resident = [to_dev(b) for b in pool]
+    static_graph = None if batched else Graph(resident[0]["src"], resident[0]["dst"], resident[0]["n"], need_eid=False)
+
+    def step(b):
+        for p in params:
+            p.grad = None
+        g = static_graph if static_graph is not None else Graph(b["src"], b["dst"], b["n"], need_eid=b["etype"] is not None)
+        h = b["x"]
+        for layer in layers:
+            gl, ef = drop(g, b["etype"])
+            h = layer(gl, h, ef) if ef is not None else layer(gl, h)
+        check = h.detach().sum(dtype=torch.float32)
+        h.backward(b["gout"])
+        if dp:      # ONE flat all-reduce of every weight gradient (SURVEY §8e)
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        return check
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush_buf = torch.empty(1 << 28, dtype=torch.uint8, device=dev)      # 256 MiB > 126 MB L2
+
+    def timed(fn, steps):
+        barrier()
+        evs = []
+        for i in range(steps):
+            flush_buf.fill_(1)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            fn(i)
+            t1.record()
+            evs.append((t0, t1))
+        barrier()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for i in range(args.warmup):
+        step(resident[i % len(resident)])
+    sampler = ClockSampler(local) if rank == 0 else None
+    function.EDGE_TIMERS = []
+    launches0 = _lib.launch_count()
+    ms_step = timed(lambda i: step(resident[i % len(resident)]), args.steps)
+    launches = _lib.launch_count() - launches0
+    timers, function.EDGE_TIMERS = function.EDGE_TIMERS, None
+    clocks = sampler.stop() if sampler else None
+
+    es = torch.empty((), dtype=dtype).element_size()
+    per = {}
+    for fn_name, t0, t1, rows in timers:
+        acc = per.setdefault(fn_name, [0.0, 0, 0])
+        acc[0] += t0.elapsed_time(t1)
+        acc[1] += 1
+        acc[2] += edge_bytes(fn_name, rows.num_pos, rows.n_rows, d * es, d * es if w.get("edge_types") else 0)
+    peak, peak_src = peaks()
+    stages = {}
+    for fn_name, (ms, cnt, by_all) in per.items():
+        by, avg = by_all / cnt, ms / cnt
+        stages[fn_name] = {"ms": avg, "bytes": by, "calls_per_step": cnt / args.steps, "gbs": by / avg / 1e6,
+                           "frac": by / avg / 1e6 / peak, "share_of_step": ms / (ms_step * args.steps)}
+    dom = max(stages, key=lambda k: per[k][0]) if stages else None
+
+    # ---- e2e: the batch (COO, features, bond types) from pinned host memory, loss + weight gradients read back
+    d2h = [0]
+
+    def e2e_step(i):
+        b = to_dev(pool[i % len(pool)])
+        check = step(b)
+        outs = [check.cpu()] + [p.grad.cpu() for p in params]
+        d2h[0] = sum(t.numel() * t.element_size() for t in outs)
+
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    h2d = sum(sum(v.numel() * v.element_size() for v in b.values() if torch.is_tensor(v)) for b in pool) / len(pool)
+    if not batched:
+        h2d -= (pool[0]["src"].numel() + pool[0]["dst"].numel()) * 4     # the static graph is converted once
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cstep, cedges, sample, _ = build_cpu_case(args, w)
+        t = time_cpu(cstep, 2, 1)
+        cpu = {"value": cedges / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        total_edges = edges_per_step * L * world
+        line = {
+            "metric": METRIC, "value": total_edges / (ms_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "us_per_step": ms_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": dict(workload_config(args, w), nodes_per_step=nodes_per_step, edges_per_step=edges_per_step),
+            "e2e": {"value": total_edges / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
+                    "d2h_bytes_per_step": d2h[0] * world, "ms_per_step": ms_e2e},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": None if dom is None else {
+                "bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "note": "working set fits the 126 MB L2: latency / launch-bound, read ms_per_step (SURVEY.md 8d)",
+                "stages": stages},
+            "cpu_baseline": cpu,
+        }
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args, w):
@@ -259,6 +558,17 @@ def run_gpu(args, w):
         for p in layers.parameters():
             dist.broadcast(p.data, 0)
     params = list(layers.parameters())
+    if dtype != torch.float32:
+        pass        # weights stay fp32 (master copies); the layers cast them to the table dtype per call
+
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = partition_parity_check(args, w, layers, dev, rank, world)
+        if parity["max_rel_err"] > parity["tolerance"]:
+            if rank == 0:
+                sys.stderr.write(f"parity check FAILED before timing: {json.dumps(parity)}\n")
+            dist.destroy_process_group()
+            raise SystemExit(3)
 
     # ---- graph + features -------------------------------------------------------------------
     t_build = time.perf_counter()
@@ -379,8 +689,10 @@ def run_gpu(args, w):
                         "frac": by / avg / 1e6 / peak, "share_of_step": ms / (ms_step * args.steps)}
     dom = max(stages, key=lambda k: per[k][0]) if stages else None
     traffic = None      # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if dom and world == 1 and os.path.exists(tpath):
+    import glob
+    tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    tpath = tfiles[-1] if tfiles else ""
+    if dom and world == 1 and tpath:
         with open(tpath) as f:
             tj = json.load(f)
         if tj["workload"] == {"nodes": n, "edges": e, "d": d, "dtype": w["dtype"]}:
@@ -455,7 +767,7 @@ def run_gpu(args, w):
         del x_host
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        cstep, cedges, sample = build_cpu_case(w, args.cpu_edges)
+        cstep, cedges, sample, _ = build_cpu_case(args, w)
         t = time_cpu(cstep, 2, 1)
         cpu = {"value": cedges / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
@@ -481,7 +793,7 @@ def run_gpu(args, w):
                                      "frac": tot_by / tot_ms / 1e6 / peak,
                                      "share_of_step": sum(v[0] for v in per.values()) / (ms_step * args.steps)},
                 "stages": stages},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "parity_check": parity,
             "graph_build_s": t_build, "peak_mem_gib": peak_mem, "phases_ms_per_step": phases,
         }
         emit(line)
@@ -502,7 +814,10 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="P", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's nodes/edges (debug)")
-    ap.add_argument("--cpu-edges", type=int, default=4_000_000, help="edges of the CPU sample")
+    ap.add_argument("--cpu-edges", type=int, default=7_812_500, help="edges of the CPU sample of workload P (1/256)")
+    ap.add_argument("--dtype", default=None, choices=sorted(DTYPES), help="table dtype override (A: f32 and bf16 lines)")
+    ap.add_argument("--agg", default=None, choices=["sum", "mean", "sym", "max"], help="aggregator override (C: max as published)")
+    ap.add_argument("--no-parity-check", action="store_true", help="N>1: skip the pre-timing parity gate")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunks", type=int, default=4,
                     help="N>1: destination chunks of the cross-layer K prefetch (1 = gather each K table whole)")
@@ -520,11 +835,17 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.dtype:
+        w["dtype"] = args.dtype
+    if args.agg:
+        w["agg"] = args.agg
     if args.impl == "reference":
         run_reference(args, w)
-    else:
+    elif args.workload == "P":
         run_gpu(args, w)
+    else:
+        run_small(args, w)
 
 
 if __name__ == "__main__":

@@ -222,6 +222,13 @@ int sirgcn_colsum(const void *x, int64_t ld, int64_t m, int32_t n, int32_t dtype
 int sirgcn_copy_rows(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
                      int64_t row_bytes, int64_t rows, void *stream);
 
+/* Dropout applied in place on a row table (the K / Q halves of the [N, 2·ld] projection buffer and, in backward, the
+ * dK / dQ halves): table[r, c] = keep[r*d + c] ? table[r, c] * scale : 0 (fp32 product, rounded once — ATen's fused
+ * dropout arithmetic), columns d..pad are zeroed.  keep = dense [rows, d] bytes (0 / 1), drawn by the host with
+ * the framework's own generator in the reference's order K, Q, E (/root/reference/models/conv.py:60-61,:128). */
+int sirgcn_mask_scale(void *table, int64_t pitch_bytes, const uint8_t *keep, int64_t rows, int32_t d,
+                      int32_t dtype, float scale, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * Split path for arbitrary (non-elementwise) σ, agg_type 'max'/'min', and the
  * SIRConvBase/SIREConvBase classes (conv.py:47, :137-221; dictionary-lookup/model.py:17).

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib
-from .function import EdgeAggregate, GatherAdd, SegmentReduce, SIRLayerFunction, _pad_cols
+from .function import EdgeAggregate, GatherAdd, SegmentReduce, SIRLayerFunction, _pad_cols, draw_keep_mask
 from .gemm import linear as _linear
 from .graph import as_graph
 
@@ -116,17 +116,26 @@ class SIRConv(nn.Module):
         dt_ = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else feat.dtype
         d_hid = self.linear_query.weight.shape[0] if hasattr(self.linear_query, "weight") else 0
         fits = 0 < d_hid and _pad_cols(d_hid, dt_) * torch.empty((), dtype=dt_).element_size() <= 2048
-        if agg in _SUM_LIKE and known is not None and not inner and not dropping and fits and self._plain():
-            # one autograd node for the whole layer (nn.Dropout is the identity here)
+        if agg in _SUM_LIKE and known is not None and not inner and fits and self._plain():
+            # one autograd node for the whole layer, in training mode too: the dropout masks of the two projections
+            # are drawn here, K first then Q (conv.py:60-61; the edge term's mask is the third draw, conv.py:128), and
+            # applied inside the node on the halves of the [Q|K] buffer
             dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else feat.dtype
             w, b, d, _ = self._cat_qk_weights(dt)
+            keep_q = keep_k = None
+            scale = 1.0
+            if dropping:
+                p = float(self.dropout.p)
+                keep_k = draw_keep_mask(n, d, dt, feat.device, p)
+                keep_q = draw_keep_mask(n, d, dt, feat.device, p)
+                scale = 0.0 if p >= 1 else 1.0 / (1.0 - p)
             e = self._edge_term(g, efeat)
             lr = self.linear_relation
             recompute = self.recompute_qk
             if recompute is None:     # auto: do not keep a projection larger than 4 GiB for backward
                 recompute = 2 * n * _pad_cols(d, dt) * torch.empty((), dtype=dt).element_size() > (1 << 32)
             return SIRLayerFunction.apply(feat, w, b, e, lr.weight, lr.bias, g, agg, known[0], known[1], d,
-                                          bool(recompute))
+                                          bool(recompute), keep_q, keep_k, scale)
         q, k = self._project_qk(feat.reshape(-1, feat.shape[-1]))
         e = self._edge_term(g, efeat)
         if agg in _SUM_LIKE and known is not None and not inner and fits:

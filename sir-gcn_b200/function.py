@@ -46,6 +46,33 @@ def copy_rows(dst, src):
     return dst
 
 
+def mask_scale_(table, keep, scale):
+    """in-place dropout on a row table view [n, d] (16-byte aligned, padded rows): table = keep ? table·scale : 0
+    (sirgcn_mask_scale; keep = torch.bool [n, d] contiguous)"""
+    if table.shape[0] == 0:
+        return table
+    assert keep.dtype == torch.bool and keep.is_contiguous() and keep.shape == table.shape
+    es = table.element_size()
+    with torch.cuda.device(table.device):
+        rc = _lib.lib().sirgcn_mask_scale(_lib.ptr(table), C.c_int64(_ld(table) * es), _lib.ptr(keep),
+                                          C.c_int64(table.shape[0]), C.c_int32(table.shape[1]),
+                                          C.c_int32(_lib.DTYPE_CODE[table.dtype]), C.c_float(scale),
+                                          _lib.stream_ptr(table.device))
+    _lib.check(rc, "sirgcn_mask_scale")
+    return table
+
+
+def draw_keep_mask(n, d, dtype, device, p):
+    """the keep mask nn.Dropout(p) would draw for a fresh contiguous [n, d] tensor of `dtype` in training mode, with
+    the framework's own generator (same Philox consumption: ATen's fused dropout keys its random stream on numel,
+    dtype and alignment only) — so a seeded run draws the very masks the reference's `self.dropout(...)` calls draw,
+    in whatever order the caller asks for them (/root/reference/models/conv.py:60-61,:128: K, Q, E)"""
+    if p >= 1:
+        return torch.zeros((n, d), dtype=torch.bool, device=device)      # nn.Dropout(1): zeros, no random numbers
+    _, keep = torch.native_dropout(torch.empty((n, d), dtype=dtype, device=device), p, True)
+    return keep
+
+
 def _table_ok(t):
     es = t.element_size()
     if t.dim() != 2 or t.stride(1) != 1 or t.data_ptr() % 16:
@@ -201,7 +228,10 @@ class SIRLayerFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
-    def forward(ctx, feat, w_qk, b_qk, e, w_r, b_r, graph, agg_type, act, act_param, d, recompute_qk=False):
+    def forward(ctx, feat, w_qk, b_qk, e, w_r, b_r, graph, agg_type, act, act_param, d, recompute_qk=False,
+                keep_q=None, keep_k=None, drop_scale=1.0):
+        """keep_q / keep_k (torch.bool [N, d], or None): training-mode dropout of the two projections
+        (conv.py:60-61), applied in place on the halves of the [Q|K] buffer; backward masks dQ / dK the same way."""
         from . import gemm
         if not feat.is_cuda:
             raise RuntimeError("SIR-GCN kernels need CUDA tensors (no CPU fallback)")
@@ -211,6 +241,9 @@ class SIRLayerFunction(torch.autograd.Function):
         ldp = qk.shape[1] // 2
         q, k = qk[:, :d], qk[:, ldp:ldp + d]
         q._sirgcn_padded = k._sirgcn_padded = True
+        if keep_k is not None:
+            mask_scale_(k, keep_k, drop_scale)
+            mask_scale_(q, keep_q, drop_scale)
         if e is not None:
             e = as_table(e.detach().to(qk.dtype))
         ds, ss = graph.scales(agg_type)
@@ -221,8 +254,9 @@ class SIRLayerFunction(torch.autograd.Function):
             del q, k
             qk = None
         out = gemm.linear_forward(a, w_r, b_r)
-        ctx.save_for_backward(feat, qk, e, a, w_qk, w_r, b_qk if recompute_qk else None)
+        ctx.save_for_backward(feat, qk, e, a, w_qk, w_r, b_qk if recompute_qk else None, keep_q, keep_k)
         ctx.graph, ctx.agg_type, ctx.act, ctx.act_param, ctx.d = graph, agg_type, act, act_param, d
+        ctx.drop_scale = drop_scale
         ctx.has_bias = (b_qk is not None, b_r is not None)
         ctx.lean = bool(recompute_qk)      # the re-made [Q|K] belongs to backward alone: it may be overwritten
         return out
@@ -231,13 +265,17 @@ class SIRLayerFunction(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gout):
         from . import gemm
-        feat, qk, e, a, w_qk, w_r, b_qk = ctx.saved_tensors
+        feat, qk, e, a, w_qk, w_r, b_qk, keep_q, keep_k = ctx.saved_tensors
         g, d = ctx.graph, ctx.d
-        if qk is None:
+        remade = qk is None
+        if remade:
             qk = gemm.linear_forward(feat, w_qk, b_qk)
         ldp = qk.shape[1] // 2
         q, k = qk[:, :d], qk[:, ldp:ldp + d]
         q._sirgcn_padded = k._sirgcn_padded = True
+        if remade and keep_k is not None:
+            mask_scale_(k, keep_k, ctx.drop_scale)
+            mask_scale_(q, keep_q, ctx.drop_scale)
         need = ctx.needs_input_grad
         gout = gout.to(qk.dtype)
         gout = gout if gout.stride(-1) == 1 else gout.contiguous()
@@ -270,10 +308,15 @@ class SIRLayerFunction(torch.autograd.Function):
             edge_backward_k(g.csc, q, k, e, da, None, ss, ctx.act, ctx.act_param, out=dk)
             del da
         del q, k, qk
+        if keep_k is not None:                 # d(dropout): the same masks on the two gradient halves
+            hq, hk = dqk[:, :d], dqk[:, ldp:ldp + d]
+            hq._sirgcn_padded = hk._sirgcn_padded = True
+            mask_scale_(hk, keep_k, ctx.drop_scale)
+            mask_scale_(hq, keep_q, ctx.drop_scale)
         dw_qk = gemm.linear_wgrad(dqk, feat, w_qk.dtype) if need[1] else None
         db_qk = gemm.column_sum(dqk, w_qk.dtype) if (need[2] and ctx.has_bias[0]) else None
         dfeat = gemm.linear_dgrad(dqk, w_qk.to(dqk.dtype)).to(feat.dtype) if need[0] else None
-        return dfeat, dw_qk, db_qk, de, dw_r, db_r, None, None, None, None, None, None
+        return dfeat, dw_qk, db_qk, de, dw_r, db_r, None, None, None, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------

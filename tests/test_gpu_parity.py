@@ -424,6 +424,71 @@ def test_contexts_no_grad_eval_deterministic_autocast():
     assert not hasattr(g, "ndata")
 
 
+class _ReplayDropout(nn.Module):
+    """stands in for nn.Dropout inside the oracle: multiplies by pre-drawn masks, in call order"""
+
+    def __init__(self, masks):
+        super().__init__()
+        self.masks = list(masks)
+
+    def forward(self, x):
+        return x * self.masks.pop(0).to(x.dtype)
+
+
+@pytest.mark.parametrize("edge", [False, True])
+@pytest.mark.parametrize("recompute", [False, True])
+@pytest.mark.parametrize("d", [64, 75])
+def test_dropout_inside_the_fused_node(edge, recompute, d):
+    """training mode keeps the whole-layer node (the published arxiv recipe trains with feat_dropout=0.2,
+    benchmark-datasets/ogbn-arxiv/train.py:303): the masks are the ones nn.Dropout would draw for the reference's
+    calls in the reference's order K, Q, E (conv.py:60-61,:128) — replayed into the fp64 oracle — and every gradient
+    carries them."""
+    from sirgcn_b200 import function
+    n, e, p = 300, 2600, 0.3
+    src, dst = rand_graph(n, e, 41, hub=5)
+    g = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
+    torch.manual_seed(3)
+    if edge:
+        layer = SIREConv(24, 3, d, 16, nn.LeakyReLU(0.2), dropout=p, agg_type="sym").to(DEV)
+        ref = RefSIREConv(24, 3, d, 16, nn.LeakyReLU(0.2), dropout=p, agg_type="sym")
+    else:
+        layer = SIRConv(24, d, 16, nn.LeakyReLU(0.2), dropout=p, agg_type="sym").to(DEV)
+        ref = RefSIRConv(24, d, 16, nn.LeakyReLU(0.2), dropout=p, agg_type="sym")
+    ref.load_state_dict({k: v.cpu() for k, v in layer.state_dict().items()})
+    layer.recompute_qk = recompute
+    layer.train()
+    x = torch.randn(n, 24, device=DEV, requires_grad=True)
+    ef = torch.randn(e, 3, device=DEV, requires_grad=True) if edge else None
+    gout = torch.randn(n, 16, device=DEV)
+    calls = []
+    orig = function.SIRLayerFunction.apply
+    function.SIRLayerFunction.apply = staticmethod(lambda *a: (calls.append(1), orig(*a))[1])
+    try:
+        torch.manual_seed(77)
+        out = layer(g, x, ef) if edge else layer(g, x)
+    finally:
+        function.SIRLayerFunction.apply = orig
+    assert calls, "training mode must take the whole-layer node"
+    wrt = [x] + ([ef] if edge else []) + list(layer.parameters())
+    grads = torch.autograd.grad(out, wrt, gout)
+    # the masks of the reference's three nn.Dropout calls, drawn with the same generator state
+    torch.manual_seed(77)
+    ones = torch.ones(n, d, device=DEV)
+    masks = [torch.nn.functional.dropout(ones, p, True).cpu().double(), torch.nn.functional.dropout(ones, p, True).cpu().double()]
+    if edge:
+        masks.append(torch.nn.functional.dropout(torch.ones(e, d, device=DEV), p, True).cpu().double())
+    assert 0.5 < masks[0].ne(0).double().mean() < 0.9 and not torch.equal(masks[0], masks[1])
+    ref = ref.double()
+    ref.dropout = _ReplayDropout(masks)
+    xr = x.detach().cpu().double().requires_grad_(True)
+    er = ef.detach().cpu().double().requires_grad_(True) if edge else None
+    out_r = ref(RefGraph(src, dst, n), xr, er) if edge else ref(RefGraph(src, dst, n), xr)
+    grads_r = torch.autograd.grad(out_r, [xr] + ([er] if edge else []) + list(ref.parameters()), gout.cpu().double())
+    assert rel_err(out, out_r) < FP32_RTOL
+    for a, b in zip(grads, grads_r):
+        assert rel_err(a, b) < FP32_RTOL
+
+
 @pytest.mark.parametrize("dtype,d", [(torch.float32, 64), (torch.bfloat16, 128), (torch.float32, 75)])
 def test_recompute_lean_backward_is_bit_identical(dtype, d):
     """recompute_qk (auto for tables > 4 GiB): [Q|K] is re-made in backward and dK is written in place over K
