@@ -342,7 +342,10 @@ def partition_parity_check(args, w, layers, dev, rank, world):
         from oracle.sirconv_ref import RefGraph, RefSIRConv
         torch.set_num_threads(os.cpu_count() or 1)
         ref = small_layers(w, RefSIRConv, None).double()
-        ref.load_state_dict({k: v.detach().cpu().double() for k, v in layers.state_dict().items()})
+        # what the reference run in the table dtype sees: weights and stored tables rounded to it (oracle header)
+        ref.load_state_dict({k: v.detach().to(dtype).cpu().double() for k, v in layers.state_dict().items()})
+        for l in ref:
+            l.storage_dtype = None if dtype == torch.float32 else dtype
         xr = x.detach().cpu().double().requires_grad_(True)
         h = xr
         rg = RefGraph(src.cpu().long(), dst.cpu().long(), n)
@@ -412,12 +415,13 @@ def run_small(args, w):
         return {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in b.items()}
 
     resident = [to_dev(b) for b in pool]
-    static_graph = None if batched else Graph(resident[0]["src"], resident[0]["dst"], resident[0]["n"], need_eid=False)
+    need_eid = bool(w.get("edge_types")) or w["agg"] in ("max", "min")      # edge ids: edge features and the split path
+    static_graph = None if batched else Graph(resident[0]["src"], resident[0]["dst"], resident[0]["n"], need_eid=need_eid)
 
     def step(b):
         for p in params:
             p.grad = None
-        g = static_graph if static_graph is not None else Graph(b["src"], b["dst"], b["n"], need_eid=b["etype"] is not None)
+        g = static_graph if static_graph is not None else Graph(b["src"], b["dst"], b["n"], need_eid=need_eid)
         h = b["x"]
         for layer in layers:
             gl, ef = drop(g, b["etype"])
@@ -472,7 +476,7 @@ def run_small(args, w):
         acc = per.setdefault(fn_name, [0.0, 0, 0])
         acc[0] += t0.elapsed_time(t1)
         acc[1] += 1
-        acc[2] += edge_bytes(fn_name, rows.num_pos, rows.n_rows, d * es, d * es if w.get("edge_types") else 0)
+        acc[2] += edge_bytes(fn_name, rows[0], rows[1], d * es, d * es if w.get("edge_types") else 0)
     peak, peak_src = peaks()
     stages = {}
     for fn_name, (ms, cnt, by_all) in per.items():
@@ -680,7 +684,7 @@ def run_gpu(args, w):
         acc = per.setdefault(name, [0.0, 0, 0])
         acc[0] += t0.elapsed_time(t1)
         acc[1] += 1
-        acc[2] += edge_bytes(name, rows.num_pos, rows.n_rows, d * es)
+        acc[2] += edge_bytes(name, rows[0], rows[1], d * es)
     peak, peak_src = peaks()
     stages = {}
     for name, (ms, cnt, by_all) in per.items():

@@ -88,9 +88,23 @@ def _norms(graph: RefGraph, agg: str, like: torch.Tensor):
     return i.reshape(shape), o.reshape(shape)
 
 
+def _store(t, dtype):
+    """round to the table dtype and come back (straight-through for autograd); identity when dtype is None"""
+    if dtype is None or t is None:
+        return t
+    return t + (t.detach().to(dtype).to(t.dtype) - t.detach())
+
+
 class RefSIRConv(nn.Module):
     """Restatement of SIRConv (conv.py:7-67): same constructor, sub-module names
-    and state_dict, so weights can be moved to/from the CUDA layer verbatim."""
+    and state_dict, so weights can be moved to/from the CUDA layer verbatim.
+
+    ``storage_dtype`` (None by default = the plain layer) models the reference run in 16-bit (``model.bfloat16()`` /
+    autocast): the projections eq / ek / e, the aggregate and the output are ROUNDED to that dtype where the 16-bit
+    run stores them, while this oracle keeps evaluating in fp64.  With a discontinuous σ' (ReLU) the sign of
+    z = eq + ek is decided by the rounded values, so a 16-bit run can only be compared with an oracle that rounds
+    at the same places."""
+    storage_dtype = None
 
     def __init__(self, input_dim, hidden_dim, output_dim, activation, dropout=0,
                  inner_bias=True, outer_bias=True, agg_type="sum"):
@@ -108,17 +122,18 @@ class RefSIRConv(nn.Module):
     def forward(self, graph: RefGraph, feat, efeat=None):
         agg = self._agg_type
         in_norm, out_norm = _norms(graph, agg, feat)
-        ek = self.dropout(self.linear_key(feat))          # conv.py:60 (K first)
-        eq = self.dropout(self.linear_query(feat))        # conv.py:61
+        sd = self.storage_dtype
+        ek = _store(self.dropout(self.linear_key(feat)), sd)          # conv.py:60 (K first)
+        eq = _store(self.dropout(self.linear_query(feat)), sd)        # conv.py:61
         z = eq.index_select(0, graph.dst) + ek.index_select(0, graph.src)
-        e = self._edge_term(graph, efeat)
+        e = _store(self._edge_term(graph, efeat), sd)
         if e is not None:
             z = z + e                                     # conv.py:111
         if agg in ("sum", "mean", "sym"):
             m = out_norm.index_select(0, graph.src) * in_norm.index_select(0, graph.dst) * self.activation(z)
-            return self.linear_relation(_reduce(graph, m, agg))   # conv.py:63-65
+            return _store(self.linear_relation(_store(_reduce(graph, m, agg), sd)), sd)   # conv.py:63-65
         m = self.linear_relation(self.activation(z))      # conv.py:47
-        return _reduce(graph, m, agg)
+        return _store(_reduce(graph, m, agg), sd)
 
 
 class RefSIREConv(RefSIRConv):

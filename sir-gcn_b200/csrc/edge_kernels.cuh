@@ -21,6 +21,9 @@
 #pragma once
 #include "common.cuh"
 
+#include <climits>
+#include <cstdlib>
+
 namespace sirgcn {
 namespace {
 
@@ -96,6 +99,34 @@ template <> __device__ __forceinline__ void add_vec<__half>(const uint4 &raw, co
 }
 #undef SIRGCN_MIXED_ADD
 
+// ---- packed 2 x 16-bit helpers of the ReLU fold (see edge_walk_kernel, FOLD) ----------------------------------
+// max / compare / add on both halves of a 32-bit register at once (SASS HMNMX2 / HSET2 / HADD2[.BF16_V2])
+template <typename T> struct Pk;
+template <> struct Pk<float> {      // never instantiated with FOLD; keeps the templates well-formed
+    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t) { return a; }
+    static __device__ __forceinline__ uint32_t gt2(uint32_t a, uint32_t) { return a; }
+    static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t) { return a; }
+};
+template <> struct Pk<__nv_bfloat16> {
+    using V = __nv_bfloat162;
+    static __device__ __forceinline__ V v(uint32_t x) { return *reinterpret_cast<V *>(&x); }
+    static __device__ __forceinline__ uint32_t u(V x) { return *reinterpret_cast<uint32_t *>(&x); }
+    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return u(__hmax2(v(a), v(b))); }
+    static __device__ __forceinline__ uint32_t gt2(uint32_t a, uint32_t b) { return u(__hgt2(v(a), v(b))); }   // 1.0 / 0.0
+    static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return u(__hadd2(v(a), v(b))); }
+};
+template <> struct Pk<__half> {
+    using V = __half2;
+    static __device__ __forceinline__ V v(uint32_t x) { return *reinterpret_cast<V *>(&x); }
+    static __device__ __forceinline__ uint32_t u(V x) { return *reinterpret_cast<uint32_t *>(&x); }
+    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return u(__hmax2(v(a), v(b))); }
+    static __device__ __forceinline__ uint32_t gt2(uint32_t a, uint32_t b) { return u(__hgt2(v(a), v(b))); }
+    static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return u(__hadd2(v(a), v(b))); }
+};
+// largest row / chunk length whose per-element edge count is exact in a 16-bit float (8 / 11 significand bits)
+template <typename T> constexpr int fold_max_threshold() { return sizeof(T) == 2 ? 2048 : 0; }
+template <> constexpr int fold_max_threshold<__nv_bfloat16>() { return 256; }
+
 // ---- activations as compile-time functors (a runtime switch per element costs issue slots) -------------
 template <int ACT> struct Act;
 template <> struct Act<SIRGCN_ACT_RELU> {
@@ -152,8 +183,26 @@ __host__ __device__ inline int lanes_per_row(int nvec, int vpl) {
 //   hot loop : S-stage cp.async ring over the batch list; neighbour ids of the next batch are fetched
 //              straight into registers one iteration ahead (the lanes of a group read the same word).
 // =====================================================================================================
-template <typename T, int VPL, int MODE, bool HAS_E, int ACT, bool GS>
-__global__ void __launch_bounds__(kWarps * 32, SIRGCN_MIN_CTAS) edge_walk_kernel(const sirgcn_edge_args a, const int chunk_mode) {
+//
+// FOLD (ReLU on 16-bit tables, no per-edge scale, no edge term; forward and dQ walks): the issue-bound short-row
+// path spends a third of its instructions on z = q + k, σ and the accumulate.  For ReLU they fold algebraically:
+//     forward   Σ_v relu(q + k_v) = Σ_v max(k_v, -q) + deg·q     max on PACKED pairs is exact (no rounding), the
+//                                                                fp32 accumulate reads the packed halves directly
+//     dQ        Σ_v [q + k_v > 0]·g = g ⊙ #{v : k_v > -q}        a packed compare + a packed count (exact up to
+//                                                                256 in bf16 / 2048 in fp16 >= the chunk length)
+// 1.5 and 1 instructions per element and edge instead of 3; the sign test is the exact one (fl(q+k) > 0 <=> k > -q).
+constexpr int kCtrSlots = 4096;
+__device__ unsigned int g_unit_ctr[kCtrSlots];                   // work-unit counters of the persistent walks
+std::atomic<unsigned int> g_ctr_next{0};
+
+// resident CTAs per SM the register allocation must allow: 8 (64 registers) for the one-vector-per-lane variants
+// without an edge term — they fit without spilling and shared memory allows 8 —, SIRGCN_MIN_CTAS (6) for the rest
+template <int VPL, bool HAS_E> constexpr int min_ctas() { return (VPL == 1 && !HAS_E) ? 8 : SIRGCN_MIN_CTAS; }
+
+template <typename T, int VPL, int MODE, bool HAS_E, int ACT, bool GS, bool FOLD = false>
+__global__ void __launch_bounds__(kWarps * 32, min_ctas<VPL, HAS_E>()) edge_walk_kernel(const sirgcn_edge_args a, const int chunk_mode,
+                                                                                       unsigned int *__restrict__ unit_ctr) {
+    static_assert(!FOLD || (ACT == SIRGCN_ACT_RELU && !GS && !HAS_E && MODE != kBwdK && sizeof(T) == 2), "FOLD preconditions");
     using C = Cfg<T, VPL, MODE, HAS_E, GS>;
     constexpr int NE = C::NE, U = C::U, S = C::S;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -176,52 +225,58 @@ __global__ void __launch_bounds__(kWarps * 32, SIRGCN_MIN_CTAS) edge_walk_kernel
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(wsm) + lane * 16;   // this lane's 16-B column of the ring
     const uint32_t ring4 = (uint32_t)__cvta_generic_to_shared(wsm) + lane * 4;   // this lane's 4-B column
 
-    // ---- which rows -------------------------------------------------------------------------------------
-    const int unit = blockIdx.x * kWarps + warp;
-    int r_beg, nrows;
+    // ---- which rows: PERSISTENT warps — every warp owns its shared-memory region and never synchronises with the
+    // others, so each warp loops over work units on its own, taking the next unit number from a device counter
+    // (units are handed out in index order, like CTAs of a plain grid: same L2 locality, no tail imbalance; the
+    // counter's latency hides under the unit being walked).  A grid of exactly the resident CTAs removes the CTA
+    // launch / drain gaps of one-CTA-per-4-tiles grids (ncu r01: 36 % achieved occupancy of 50 % theoretical).
+    // unit_ctr == nullptr: plain grid, one unit per warp. ---------------------------------------------------------
+    const int n_units = chunk_mode ? a.n_chunks : a.n_tiles;
+    int unit = 0, r_beg = 0, nrows = 0, total = 0;
     const bool write_scaled = MODE == kBwdQ && a.da_scaled != nullptr && !chunk_mode;   // long rows: finalize kernel
-    if (chunk_mode) {
-        if (unit >= a.n_chunks) return;
-        r_beg = a.sched.long_rows[a.sched.chunk_lrow[unit]];
-        nrows = 1;
-        const int beg = a.sched.chunk_beg[unit];
-        if (lane == 0) {
-            s_ptr[0] = beg;
-            s_ptr[1] = min(beg + thr, a.indptr[r_beg + 1]);
+    auto setup = [&]() -> bool {
+        if (chunk_mode) {
+            r_beg = a.sched.long_rows[a.sched.chunk_lrow[unit]];
+            nrows = 1;
+            const int beg = a.sched.chunk_beg[unit];
+            if (lane == 0) {
+                s_ptr[0] = beg;
+                s_ptr[1] = min(beg + thr, a.indptr[r_beg + 1]);
+            }
+        } else {
+            r_beg = a.tile_row[unit];
+            nrows = a.tile_row[unit + 1] - r_beg;
+            if (nrows <= 0) return false;
+            for (int i = lane; i <= nrows; i += 32) s_ptr[i] = a.indptr[r_beg + i];
         }
-    } else {
-        if (unit >= a.n_tiles) return;
-        r_beg = a.tile_row[unit];
-        nrows = a.tile_row[unit + 1] - r_beg;
-        if (nrows <= 0) return;
-        for (int i = lane; i <= nrows; i += 32) s_ptr[i] = a.indptr[r_beg + i];
-    }
-    __syncwarp();
+        __syncwarp();
 
-    // ---- pre-pass: batch list ---------------------------------------------------------------------------
-    int total = 0;
-    for (int j0 = 0; j0 < nrows; j0 += 32) {
-        const int i = j0 + lane;
-        int beg = 0, deg = 0, nb = 0;
-        if (i < nrows) {
-            beg = s_ptr[i];
-            deg = s_ptr[i + 1] - beg;
-            if (chunk_mode || deg <= thr) nb = max(1, (deg + B - 1) >> logB);    // empty row: one batch of 0 edges (A[u] = 0)
-            if (has_rs) s_rs[i] = rscale[r_beg + i];
-        }
-        int incl = nb;
+        // ---- pre-pass: batch list -----------------------------------------------------------------------
+        total = 0;
+        for (int j0 = 0; j0 < nrows; j0 += 32) {
+            const int i = j0 + lane;
+            int beg = 0, deg = 0, nb = 0;
+            if (i < nrows) {
+                beg = s_ptr[i];
+                deg = s_ptr[i + 1] - beg;
+                if (chunk_mode || deg <= thr) nb = max(1, (deg + B - 1) >> logB);    // empty row: one batch of 0 edges (A[u] = 0)
+                if (has_rs) s_rs[i] = rscale[r_beg + i];
+            }
+            int incl = nb;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int off = total + incl - nb;
+            for (int k = 0; k < nb; ++k)
+                s_desc[off + k] = make_int2(beg + (k << logB),
+                                            i | (min(B, deg - (k << logB)) << 8) | (k == 0 ? 1 << 16 : 0) | (k == nb - 1 ? 1 << 17 : 0));
+            total += __shfl_sync(kFull, incl, 31);
         }
-        const int off = total + incl - nb;
-        for (int k = 0; k < nb; ++k)
-            s_desc[off + k] = make_int2(beg + (k << logB),
-                                        i | (min(B, deg - (k << logB)) << 8) | (k == 0 ? 1 << 16 : 0) | (k == nb - 1 ? 1 << 17 : 0));
-        total += __shfl_sync(kFull, incl, 31);
-    }
-    __syncwarp();
+        __syncwarp();
+        return true;
+    };
 
     // ---- lane constants --------------------------------------------------------------------------------------
     bool vok[VPL];
@@ -325,7 +380,9 @@ __global__ void __launch_bounds__(kWarps * 32, SIRGCN_MIN_CTAS) edge_walk_kernel
     };
 
     // ---- arithmetic of one landed batch -------------------------------------------------------------------
-    float self[VPL][NE], ds[MODE == kBwdQ ? VPL : 1][NE], acc[VPL][NE];
+    float self[FOLD ? 1 : VPL][NE], ds[MODE == kBwdQ ? VPL : 1][NE], acc[VPL][NE];
+    uint4 negq[FOLD ? VPL : 1], cntp[FOLD && MODE == kBwdQ ? VPL : 1];       // FOLD: packed -q, packed edge counts
+    int rowcnt = 0;                                                           // FOLD forward: edges of the row so far
     float rs = 1.f;
     const float ap = a.act_param;
     const float zero[NE] = {};
@@ -340,7 +397,13 @@ __global__ void __launch_bounds__(kWarps * 32, SIRGCN_MIN_CTAS) edge_walk_kernel
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
                 if (vok[v]) {
-                    add_vec<T>(lds128<C::kOffSelf>(st + v * 512), zero, self[v]);
+                    if constexpr (FOLD) {
+                        const uint4 rq = lds128<C::kOffSelf>(st + v * 512);
+                        negq[v] = make_uint4(rq.x ^ 0x80008000u, rq.y ^ 0x80008000u, rq.z ^ 0x80008000u, rq.w ^ 0x80008000u);
+                        if (MODE == kBwdQ) cntp[MODE == kBwdQ ? v : 0] = make_uint4(0u, 0u, 0u, 0u);
+                    } else {
+                        add_vec<T>(lds128<C::kOffSelf>(st + v * 512), zero, self[FOLD ? 0 : v]);
+                    }
                     if (MODE == kBwdQ) {
                         add_vec<T>(lds128<C::kOffSelf + C::kSlot>(st + v * 512), zero, ds[MODE == kBwdQ ? v : 0]);
 #pragma unroll
@@ -354,7 +417,9 @@ __global__ void __launch_bounds__(kWarps * 32, SIRGCN_MIN_CTAS) edge_walk_kernel
 #pragma unroll
                 for (int i = 0; i < NE; ++i) acc[v][i] = 0.f;
             }
+            rowcnt = 0;
         }
+        if constexpr (FOLD) rowcnt += cnt;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (slot[u] >= cnt) continue;
@@ -375,8 +440,23 @@ __global__ void __launch_bounds__(kWarps * 32, SIRGCN_MIN_CTAS) edge_walk_kernel
                     SIRGCN_LD(0) SIRGCN_LD(1) SIRGCN_LD(2) default: SIRGCN_LD(3)
 #undef SIRGCN_LD
                 }
+                if constexpr (FOLD) {
+                    const uint4 nq = negq[v];
+                    if (MODE == kFwd) {
+                        const uint4 m = make_uint4(Pk<T>::max2(r1.x, nq.x), Pk<T>::max2(r1.y, nq.y),
+                                                   Pk<T>::max2(r1.z, nq.z), Pk<T>::max2(r1.w, nq.w));
+                        add_vec<T>(m, acc[v], acc[v]);
+                    } else {
+                        uint4 &c = cntp[MODE == kBwdQ ? v : 0];
+                        c.x = Pk<T>::add2(c.x, Pk<T>::gt2(r1.x, nq.x));
+                        c.y = Pk<T>::add2(c.y, Pk<T>::gt2(r1.y, nq.y));
+                        c.z = Pk<T>::add2(c.z, Pk<T>::gt2(r1.z, nq.z));
+                        c.w = Pk<T>::add2(c.w, Pk<T>::gt2(r1.w, nq.w));
+                    }
+                    continue;
+                }
                 float z[NE];
-                add_vec<T>(r1, self[v], z);
+                add_vec<T>(r1, self[FOLD ? 0 : v], z);
                 if (HAS_E && a.e) add_vec<T>(re, z, z);
                 if (MODE == kFwd) {
 #pragma unroll
@@ -425,10 +505,39 @@ __global__ void __launch_bounds__(kWarps * 32, SIRGCN_MIN_CTAS) edge_walk_kernel
             }
         }
         if (d.y & (1 << 17)) {                                   // last batch of a row: reduce + store
-            if (VPL == 1) {
-                for (int off = 16; off >= G; off >>= 1) {
+            if constexpr (FOLD && MODE == kBwdQ) {
+                if (VPL == 1) {                                  // the lane groups' counts add up exactly (<= row length)
+                    for (int off = 16; off >= G; off >>= 1) {
+                        uint4 &c = cntp[0];
+                        c.x = Pk<T>::add2(c.x, __shfl_xor_sync(kFull, c.x, off));
+                        c.y = Pk<T>::add2(c.y, __shfl_xor_sync(kFull, c.y, off));
+                        c.z = Pk<T>::add2(c.z, __shfl_xor_sync(kFull, c.z, off));
+                        c.w = Pk<T>::add2(c.w, __shfl_xor_sync(kFull, c.w, off));
+                    }
+                }
 #pragma unroll
-                    for (int i = 0; i < NE; ++i) acc[0][i] += __shfl_xor_sync(kFull, acc[0][i], off);
+                for (int v = 0; v < VPL; ++v) {
+                    float cf[NE];
+                    add_vec<T>(cntp[MODE == kBwdQ ? v : 0], zero, cf);
+#pragma unroll
+                    for (int i = 0; i < NE; ++i) acc[v][i] = ds[MODE == kBwdQ ? v : 0][i] * cf[i];
+                }
+            } else {
+                if (VPL == 1) {
+                    for (int off = 16; off >= G; off >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < NE; ++i) acc[0][i] += __shfl_xor_sync(kFull, acc[0][i], off);
+                    }
+                }
+                if constexpr (FOLD) {                            // + deg·q  (−deg·(−q): the packed negation is at hand)
+                    const float c = -(float)rowcnt;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        float nq[NE];
+                        add_vec<T>(negq[v], zero, nq);
+#pragma unroll
+                        for (int i = 0; i < NE; ++i) acc[v][i] = fmaf(c, nq[i], acc[v][i]);
+                    }
                 }
             }
             if (gi == 0) {
@@ -460,15 +569,29 @@ __global__ void __launch_bounds__(kWarps * 32, SIRGCN_MIN_CTAS) edge_walk_kernel
     };
 
     // ---- S-stage software pipeline; one commit per iteration keeps wait_group<S-1> exact ---------------------
-    prefetch(0);
+    unsigned int ticket = 0;                                     // lane 0: the next unit of this warp
+    if (unit_ctr) {
+        if (lane == 0) ticket = atomicAdd(unit_ctr, 1u);
+        unit = (int)__shfl_sync(kFull, ticket, 0);
+    } else {
+        unit = blockIdx.x * kWarps + warp;
+    }
 #pragma unroll 1
-    for (int it = 0; it < total + S - 1; ++it) {
-        if (it < total) issue(it);
-        cp_async_commit();
-        if (it >= S - 1) {
-            cp_async_wait<S - 1>();
-            consume(it - (S - 1));
+    for (; unit < n_units; unit = unit_ctr ? (int)__shfl_sync(kFull, ticket, 0) : n_units) {
+        if (unit_ctr && lane == 0) ticket = atomicAdd(unit_ctr, 1u);       // consumed at the end of this unit
+        if (!setup()) continue;
+        istage = cstage = 0;
+        prefetch(0);
+#pragma unroll 1
+        for (int it = 0; it < total + S - 1; ++it) {
+            if (it < total) issue(it);
+            cp_async_commit();
+            if (it >= S - 1) {
+                cp_async_wait<S - 1>();
+                consume(it - (S - 1));
+            }
         }
+        __syncwarp();                                            // the next unit's pre-pass rewrites the batch list
     }
 }
 
@@ -599,7 +722,7 @@ __global__ void __launch_bounds__(256) edge_big_finalize_kernel(const sirgcn_edg
     }
 }
 
-template <typename T, int VPL, int MODE, bool HAS_E, int ACT, bool GS>
+template <typename T, int VPL, int MODE, bool HAS_E, int ACT, bool GS, bool FOLD = false>
 int launch_gs(const sirgcn_edge_args &a, cudaStream_t st) {
     using C = Cfg<T, VPL, MODE, HAS_E, GS>;
     const int nvec = (a.d * (int)sizeof(T) + 15) / 16;
@@ -610,19 +733,45 @@ int launch_gs(const sirgcn_edge_args &a, cudaStream_t st) {
         set_error("long_threshold %d needs %zu bytes of shared memory per CTA (max 232448)", a.long_threshold, smem);
         return SIRGCN_EUNSUP;
     }
-    auto kern = edge_walk_kernel<T, VPL, MODE, HAS_E, ACT, GS>;
+    auto kern = edge_walk_kernel<T, VPL, MODE, HAS_E, ACT, GS, FOLD>;
     static std::atomic<int> configured{0};           // per instantiation: raise the opt-in limit only when needed
     if ((int)smem > configured.load(std::memory_order_relaxed)) {   // (one process drives one GPU)
         SIRGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured.store((int)smem, std::memory_order_relaxed);
     }
-    if (a.n_tiles > 0) {
-        kern<<<(unsigned)((a.n_tiles + kWarps - 1) / kWarps), kWarps * 32, smem, st>>>(a, 0);
+    // persistent grid: as many CTAs as are resident at once (occupancy query, cached per instantiation and smem size)
+    static std::atomic<int> resident{0}, resident_smem{-1};
+    if (resident_smem.load(std::memory_order_relaxed) != (int)smem) {
+        int per_sm = 0;
+        SIRGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarps * 32, smem));
+        resident.store(std::max(1, per_sm) * kNumSMs, std::memory_order_relaxed);
+        resident_smem.store((int)smem, std::memory_order_relaxed);
+    }
+    static const bool no_persist = getenv("SIRGCN_NO_PERSIST") != nullptr;       // A/B measurements
+    const int cap = resident.load(std::memory_order_relaxed);
+    // unit counters: a ring of words in static device memory (the library allocates nothing); a launch zeroes its
+    // word on its own stream just before it runs, and a word comes round again only after kCtrSlots later launches
+    static unsigned int *ctr_base = nullptr;
+    if (!ctr_base) SIRGCN_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&ctr_base), g_unit_ctr));
+    auto walk = [&](int n_units, int chunk_mode) -> int {
+        const int grid_all = (n_units + kWarps - 1) / kWarps;
+        if (no_persist || grid_all <= cap) {                     // everything is resident at once anyway
+            kern<<<(unsigned)grid_all, kWarps * 32, smem, st>>>(a, chunk_mode, nullptr);
+        } else {
+            unsigned int *ctr = ctr_base + (g_ctr_next.fetch_add(1, std::memory_order_relaxed) % kCtrSlots);
+            SIRGCN_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
+            kern<<<(unsigned)cap, kWarps * 32, smem, st>>>(a, chunk_mode, ctr);
+        }
         SIRGCN_LAUNCHED();
+        return SIRGCN_OK;
+    };
+    if (a.n_tiles > 0) {
+        const int rc = walk(a.n_tiles, 0);
+        if (rc) return rc;
     }
     if (a.n_chunks > 0) {
-        kern<<<(unsigned)((a.n_chunks + kWarps - 1) / kWarps), kWarps * 32, smem, st>>>(a, 1);
-        SIRGCN_LAUNCHED();
+        const int rc = walk(a.n_chunks, 1);
+        if (rc) return rc;
         edge_long_finalize_kernel<T, MODE><<<(unsigned)((a.n_long + 7) / 8), 256, 0, st>>>(a);
         SIRGCN_LAUNCHED();
         const int big_grid = std::min(a.n_chunks / SIRGCN_BIG_CHUNKS, kNumSMs * 4);   // n_big <= n_chunks / 33
@@ -637,6 +786,11 @@ int launch_gs(const sirgcn_edge_args &a, cudaStream_t st) {
 template <typename T, int VPL, int MODE, bool HAS_E, int ACT>
 int launch_act(const sirgcn_edge_args &a, cudaStream_t st) {
     const float *gscale = MODE == kBwdK ? a.dst_scale : a.src_scale;
+    if constexpr (ACT == SIRGCN_ACT_RELU && !HAS_E && sizeof(T) == 2 && MODE != kBwdK) {
+        static const bool no_fold = getenv("SIRGCN_NO_FOLD") != nullptr;         // A/B measurements
+        if (!gscale && !no_fold && a.long_threshold <= fold_max_threshold<T>())
+            return launch_gs<T, VPL, MODE, HAS_E, ACT, false, true>(a, st);
+    }
     return gscale ? launch_gs<T, VPL, MODE, HAS_E, ACT, true>(a, st) : launch_gs<T, VPL, MODE, HAS_E, ACT, false>(a, st);
 }
 

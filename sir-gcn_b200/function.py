@@ -99,7 +99,7 @@ def _ld(t):
     return t.stride(0) if t.shape[0] > 1 else _pad_cols(t.shape[1], t.dtype)
 
 
-# bench.py sets this to a list to collect (entry point, start event, end event, rows) of every edge
+# bench.py sets this to a list to collect (entry point, start event, end event, (positions, rows)) of every edge
 # call, recorded on the stream the kernels are launched on (roofline measurement); None = off
 EDGE_TIMERS = None
 
@@ -142,7 +142,7 @@ def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da
         rc = getattr(_lib.lib(), fn_name)(C.byref(a), _lib.stream_ptr(dev))
         if EDGE_TIMERS is not None:
             t1.record()
-            EDGE_TIMERS.append((fn_name, t0, t1, rows))
+            EDGE_TIMERS.append((fn_name, t0, t1, (rows.num_pos, rows.n_rows)))   # sizes only: never keep a graph alive
     _lib.check(rc, fn_name)
 
 
