@@ -186,7 +186,20 @@ typedef struct sirgcn_edge_args {
     int32_t n_tiles;
     int32_t accumulate;     /* != 0: out[row] += result instead of out[row] = result (a row's edges split
                                over several walks, e.g. one walk per arrived source block; fixed order)  */
+    /* Edge term from a small TABLE (an nn.Embedding over edge types, benchmark-datasets/zinc/model.py:12-15): pass
+     * e = the table [n_etypes, lde] and eid[p] = the type of the edge stored at position p (so no [E, d] tensor is
+     * ever read).  In backward-dQ the table's gradient is reduced inside the walk: set de = NULL, n_etypes > 0 and
+     * de_partial = ZEROED fp32 scratch [n_tiles + n_chunks, n_etypes, ldp] (ldp as for `partial`); every work unit
+     * writes the sums of its edges per type, lane groups and units are combined in a fixed order
+     * (sirgcn_etable_grad) => bitwise repeatable, no atomics.  n_etypes <= SIRGCN_MAX_ETYPES. */
+    int32_t n_etypes;
+    float *de_partial;
 } sirgcn_edge_args;
+#define SIRGCN_MAX_ETYPES 8
+
+/* dTable[t, c] = sum over work units u (in index order) of de_partial[u, t, c]; out is fp32 [n_etypes, ld_out]. */
+int sirgcn_etable_grad(const float *de_partial, int64_t n_units, int32_t n_etypes, int32_t ldp, int32_t d,
+                       float *out, int64_t ld_out, void *stream);
 
 /* bytes of fp32 scratch needed for `partial` */
 size_t sirgcn_edge_partial_bytes(int32_t n_chunks, int32_t d, int32_t dtype);

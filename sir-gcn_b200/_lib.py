@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIRGCN_LIB") or os.path.join(_HERE, "libsirgcn.so")   # override: kernel-variant A/B runs
 
 ABI_VERSION = 8     # include/sirgcn.h SIRGCN_ABI_VERSION
+MAX_ETYPES = 8      # SIRGCN_MAX_ETYPES
 F32, BF16, F16 = 0, 1, 2
 ACT_IDENTITY, ACT_RELU, ACT_LEAKY_RELU, ACT_GELU = 0, 1, 2, 3
 
@@ -22,7 +23,7 @@ EXPORTS = (
     "sirgcn_csr_build_workspace_bytes", "sirgcn_csr_build", "sirgcn_schedule_build",
     "sirgcn_edge_subgraph_workspace_bytes", "sirgcn_edge_subgraph",
     "sirgcn_num_tiles", "sirgcn_tiles_build", "sirgcn_rows_build_workspace_bytes", "sirgcn_rows_build",
-    "sirgcn_edge_partial_bytes", "sirgcn_edge_fwd", "sirgcn_edge_bwd_q", "sirgcn_edge_bwd_k",
+    "sirgcn_edge_partial_bytes", "sirgcn_edge_fwd", "sirgcn_edge_bwd_q", "sirgcn_edge_bwd_k", "sirgcn_etable_grad",
     "sirgcn_gemm_tn", "sirgcn_colsum_workspace_bytes", "sirgcn_colsum", "sirgcn_copy_rows", "sirgcn_mask_scale", "sirgcn_gather_add", "sirgcn_segment_sum", "sirgcn_segment_minmax", "sirgcn_segment_minmax_bwd",
     "sirgcn_peer_alloc", "sirgcn_peer_free", "sirgcn_peer_open", "sirgcn_peer_close", "sirgcn_peer_copy", "sirgcn_peer_push", "sirgcn_peer_push_tma", "sirgcn_peer_barrier",
 )
@@ -49,6 +50,7 @@ class EdgeArgs(C.Structure):
         ("sched", Schedule), ("n_long", C.c_int32), ("n_chunks", C.c_int32),
         ("partial", C.c_void_p),
         ("tile_row", C.c_void_p), ("n_tiles", C.c_int32), ("accumulate", C.c_int32),
+        ("n_etypes", C.c_int32), ("de_partial", C.c_void_p),
     ]
 
 

@@ -101,6 +101,13 @@ class SIRConv(nn.Module):
     def _edge_term(self, graph, efeat):
         return None
 
+    def _edge_term_or_table(self, graph, efeat, dropping):
+        """(e, e_types) for the whole-layer node: (projected edge term [E, d], None), or — when the edge term is an
+        nn.Embedding over at most MAX_ETYPES edge types and no dropout applies to it — (the embedding TABLE, the
+        integer edge types): the kernels then look the rows up themselves and reduce the table's gradient, and no
+        [E, d] tensor exists in either direction."""
+        return self._edge_term(graph, efeat), None
+
     def forward(self, graph, feat, efeat=None):
         g = as_graph(graph)
         if feat.dim() < 2:
@@ -129,13 +136,13 @@ class SIRConv(nn.Module):
                 keep_k = draw_keep_mask(n, d, dt, feat.device, p)
                 keep_q = draw_keep_mask(n, d, dt, feat.device, p)
                 scale = 0.0 if p >= 1 else 1.0 / (1.0 - p)
-            e = self._edge_term(g, efeat)
+            e, e_types = self._edge_term_or_table(g, efeat, dropping)
             lr = self.linear_relation
             recompute = self.recompute_qk
             if recompute is None:     # auto: do not keep a projection larger than 4 GiB for backward
                 recompute = 2 * n * _pad_cols(d, dt) * torch.empty((), dtype=dt).element_size() > (1 << 32)
             return SIRLayerFunction.apply(feat, w, b, e, lr.weight, lr.bias, g, agg, known[0], known[1], d,
-                                          bool(recompute), keep_q, keep_k, scale)
+                                          bool(recompute), keep_q, keep_k, scale, e_types)
         q, k = self._project_qk(feat.reshape(-1, feat.shape[-1]))
         e = self._edge_term(g, efeat)
         if agg in _SUM_LIKE and known is not None and not inner and fits:
@@ -170,6 +177,17 @@ class SIREConv(SIRConv):
         if efeat.shape[0] != graph.num_edges():
             raise ValueError(f"efeat has {efeat.shape[0]} rows but the graph has {graph.num_edges()} edges")
         return self.dropout(self.linear_edge(efeat))    # conv.py:128 (third dropout draw)
+
+    def _edge_term_or_table(self, graph, efeat, dropping):
+        le = self.linear_edge
+        if (type(le) is nn.Embedding and not dropping and le.num_embeddings <= _lib.MAX_ETYPES and le.padding_idx is None
+                and le.max_norm is None and not le.scale_grad_by_freq and not le.sparse
+                and torch.is_tensor(efeat) and efeat.dim() == 1 and not efeat.is_floating_point()
+                and not efeat.dtype == torch.bool):
+            if efeat.shape[0] != graph.num_edges():
+                raise ValueError(f"efeat has {efeat.shape[0]} rows but the graph has {graph.num_edges()} edges")
+            return le.weight, efeat
+        return self._edge_term(graph, efeat), None
 
     def forward(self, graph, nfeat, efeat):
         return super().forward(graph, nfeat, efeat)

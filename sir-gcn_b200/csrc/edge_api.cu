@@ -41,6 +41,11 @@ int validate(const sirgcn_edge_args *a, int mode) {
         SIRGCN_CHECK_ARG(a->eid != nullptr, "dE requested without edge ids");
         SIRGCN_CHECK_ARG(aligned16(a->de) && a->ldde >= ldmin && (a->ldde * es) % 16 == 0, "bad dE table");
     }
+    if (mode == kBwdQ && a->n_etypes > 0 && a->de_partial) {
+        SIRGCN_CHECK_ARG(a->n_etypes <= SIRGCN_MAX_ETYPES && a->eid != nullptr && a->de == nullptr && aligned16(a->de_partial),
+                         "table-gradient mode needs n_etypes <= %d, edge types in eid, de == NULL and aligned scratch",
+                         SIRGCN_MAX_ETYPES);
+    }
     if (mode == kBwdQ && a->da_scaled) {
         SIRGCN_CHECK_ARG(aligned16(a->da_scaled) && a->ldds >= ldmin && (a->ldds * es) % 16 == 0, "bad scaled-dA table");
     }
@@ -83,6 +88,40 @@ size_t sirgcn_edge_partial_bytes(int32_t n_chunks, int32_t d, int32_t dtype) {
     const int es = sirgcn::elem_size(dtype);
     const size_t nvec = ((size_t)d * es + 15) / 16;
     return (size_t)n_chunks * nvec * (16 / es) * sizeof(float);
+}
+
+namespace sirgcn {
+namespace {
+// one thread per (type, column): units summed in index order by 8 interleaved partial sums, combined in order
+__global__ void __launch_bounds__(256) etable_grad_kernel(const float *__restrict__ part, int64_t n_units, int n_types,
+                                                          int ldp, int d, float *__restrict__ out, int64_t ld_out) {
+    __shared__ float sm[8][32];
+    const int col = blockIdx.x * 32 + threadIdx.x, t = blockIdx.y, y = threadIdx.y;
+    float s = 0.f;
+    if (col < d)
+        for (int64_t u = y; u < n_units; u += 8) s += part[(u * n_types + t) * ldp + col];
+    sm[y][threadIdx.x] = s;
+    __syncthreads();
+    if (y == 0 && col < d) {
+        float r = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r += sm[j][threadIdx.x];
+        out[(int64_t)t * ld_out + col] = r;
+    }
+}
+}  // namespace
+}  // namespace sirgcn
+
+int sirgcn_etable_grad(const float *de_partial, int64_t n_units, int32_t n_etypes, int32_t ldp, int32_t d,
+                       float *out, int64_t ld_out, void *stream) {
+    using namespace sirgcn;
+    SIRGCN_CHECK_ARG(n_units >= 0 && n_etypes > 0 && n_etypes <= SIRGCN_MAX_ETYPES && d > 0 && ldp >= d && ld_out >= d,
+                     "bad n_units/n_etypes/d/ldp/ld_out");
+    SIRGCN_CHECK_ARG(out && (de_partial || n_units == 0), "out/de_partial is NULL");
+    etable_grad_kernel<<<dim3((unsigned)((d + 31) / 32), (unsigned)n_etypes), dim3(32, 8), 0,
+                         reinterpret_cast<cudaStream_t>(stream)>>>(de_partial, n_units, n_etypes, ldp, d, out, ld_out);
+    SIRGCN_LAUNCHED();
+    return SIRGCN_OK;
 }
 
 int sirgcn_edge_fwd(const sirgcn_edge_args *args, void *stream) { return sirgcn::dispatch(args, sirgcn::kFwd, stream); }

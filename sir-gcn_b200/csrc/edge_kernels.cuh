@@ -218,10 +218,15 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<VPL, HAS_E>()) edge_walk
     const int thr = a.long_threshold;
     const int cap = desc_cap(thr, B);
 
-    unsigned char *wsm = smem_raw + (size_t)warp * (S * C::kStage + tail_bytes(cap));
+    // table-gradient mode (dQ walk, edge term from a small table): per-warp fp32 accumulators [type][VPL][lane][NE],
+    // every lane owns its 16-byte... NE-float slot => no conflicts, no atomics, fixed order
+    const int n_et = (C::DE && a.de == nullptr && a.de_partial != nullptr) ? a.n_etypes : 0;
+    const int tacc_bytes = n_et * VPL * 32 * NE * (int)sizeof(float);
+    unsigned char *wsm = smem_raw + (size_t)warp * (S * C::kStage + tail_bytes(cap) + tacc_bytes);
     int2 *s_desc = reinterpret_cast<int2 *>(wsm + S * C::kStage);
     int *s_ptr = reinterpret_cast<int *>(s_desc + cap);
     float *s_rs = reinterpret_cast<float *>(s_ptr + kTileRowCap + 4);
+    float *s_tacc = reinterpret_cast<float *>(wsm + S * C::kStage + tail_bytes(cap)) + lane * NE;   // this lane's slot of type 0, vector 0
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(wsm) + lane * 16;   // this lane's 16-B column of the ring
     const uint32_t ring4 = (uint32_t)__cvta_generic_to_shared(wsm) + lane * 4;   // this lane's 4-B column
 
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<VPL, HAS_E>()) edge_walk
     const uint32_t ldself = (uint32_t)((MODE == kBwdK ? a.ldk : a.ldq) * esz);
     const char *etab = HAS_E ? reinterpret_cast<const char *>(a.e) + li * 16 : nullptr;
     const uint32_t lde = (uint32_t)(a.lde * esz);
-    char *detab = C::DE ? reinterpret_cast<char *>(a.de) + li * 16 : nullptr;
+    char *detab = (C::DE && a.de) ? reinterpret_cast<char *>(a.de) + li * 16 : nullptr;   // NULL: no dE rows wanted
     const int32_t *idxp = a.idx + gi * Ueff;
     const int32_t *eidp = HAS_E ? a.eid + gi * Ueff : nullptr;
     const int vstride = G * 16;                                  // bytes between a lane's consecutive vectors of one row
@@ -495,10 +500,20 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<VPL, HAS_E>()) edge_walk
                         acc[v][i] += val[i];
                     }
                     if (C::DE) {
-                        if (detab) {
+                        if (detab || n_et) {
                             const int eidv = (int)(u == 0 ? lds32<C::kOffEid>(st4) : u == 1 ? lds32<C::kOffEid + 128>(st4)
                                                    : u == 2 ? lds32<C::kOffEid + 256>(st4) : lds32<C::kOffEid + 384>(st4));
-                            stg_vec(detab + (uint64_t)(uint32_t)eidv * (uint32_t)(a.ldde * esz) + v * vstride, pack<T>(val));
+                            if (detab) {
+                                stg_vec(detab + (uint64_t)(uint32_t)eidv * (uint32_t)(a.ldde * esz) + v * vstride, pack<T>(val));
+                            } else {                             // eidv = the edge's TYPE: add into this lane's slot
+                                float *t = s_tacc + (eidv * VPL + v) * (32 * NE);
+#pragma unroll
+                                for (int i = 0; i < NE; i += 4) {
+                                    float4 c = *reinterpret_cast<float4 *>(t + i);
+                                    c.x += val[i]; c.y += val[i + 1]; c.z += val[i + 2]; c.w += val[i + 3];
+                                    *reinterpret_cast<float4 *>(t + i) = c;
+                                }
+                            }
                         }
                     }
                 }
@@ -581,6 +596,11 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<VPL, HAS_E>()) edge_walk
         if (unit_ctr && lane == 0) ticket = atomicAdd(unit_ctr, 1u);       // consumed at the end of this unit
         if (!setup()) continue;
         istage = cstage = 0;
+        if (C::DE && n_et) {                                     // zero this lane's slots
+            for (int j = 0; j < n_et * VPL; ++j)
+#pragma unroll
+                for (int i = 0; i < NE; i += 4) *reinterpret_cast<float4 *>(s_tacc + j * (32 * NE) + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         prefetch(0);
 #pragma unroll 1
         for (int it = 0; it < total + S - 1; ++it) {
@@ -592,6 +612,30 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<VPL, HAS_E>()) edge_walk
             }
         }
         __syncwarp();                                            // the next unit's pre-pass rewrites the batch list
+        if (C::DE && n_et) {
+            // this unit's sums per edge type: the lane groups are combined in group order by the lanes of group 0
+            if (gi == 0 && vok[0]) {
+                const int width = nvec * NE;
+                float *o = a.de_partial + ((int64_t)(unit + (chunk_mode ? a.n_tiles : 0)) * n_et) * width + li * NE;
+                for (int t = 0; t < n_et; ++t) {
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        if (!vok[v]) continue;
+                        float r[NE];
+#pragma unroll
+                        for (int i = 0; i < NE; ++i) r[i] = 0.f;
+                        const float *src = s_tacc + (t * VPL + v) * (32 * NE);
+                        for (int gg = 0; gg < NG; ++gg)
+#pragma unroll
+                            for (int i = 0; i < NE; ++i) r[i] += src[gg * G * NE + i];
+#pragma unroll
+                        for (int i = 0; i < NE; i += 4)
+                            *reinterpret_cast<float4 *>(o + (int64_t)t * width + v * G * NE + i) = make_float4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -728,7 +772,10 @@ int launch_gs(const sirgcn_edge_args &a, cudaStream_t st) {
     const int nvec = (a.d * (int)sizeof(T) + 15) / 16;
     const int NG = 32 / lanes_per_row(nvec, VPL);
     const int B = NG * std::min(C::U, 32 / NG);
-    const size_t smem = (size_t)kWarps * (C::S * C::kStage + tail_bytes(desc_cap(a.long_threshold, B)));
+    static const size_t smem_pad = getenv("SIRGCN_SMEM_PAD") ? (size_t)atoi(getenv("SIRGCN_SMEM_PAD")) : 0;   // occupancy experiments
+    const int n_et = (C::DE && a.de == nullptr && a.de_partial != nullptr) ? a.n_etypes : 0;
+    const size_t smem = (size_t)kWarps * (C::S * C::kStage + tail_bytes(desc_cap(a.long_threshold, B)) +
+                                          (size_t)n_et * VPL * 32 * VecTraits<T>::N * sizeof(float)) + smem_pad;
     if (smem > 227 * 1024) {
         set_error("long_threshold %d needs %zu bytes of shared memory per CTA (max 232448)", a.long_threshold, smem);
         return SIRGCN_EUNSUP;
@@ -811,7 +858,7 @@ int launch_mode(const sirgcn_edge_args &a, cudaStream_t st) {
 template <typename T, int MODE>
 int launch_vpl(const sirgcn_edge_args &a, cudaStream_t st) {
     const int nvec = (a.d * (int)sizeof(T) + 15) / 16;
-    const bool has_e = a.e != nullptr || (MODE == kBwdQ && a.de != nullptr);
+    const bool has_e = a.e != nullptr || (MODE == kBwdQ && (a.de != nullptr || (a.n_etypes > 0 && a.de_partial != nullptr)));
 #define SIRGCN_LAUNCH_VPL(V) (has_e ? launch_mode<T, V, MODE, true>(a, st) : launch_mode<T, V, MODE, false>(a, st))
     if (nvec <= 32) return SIRGCN_LAUNCH_VPL(1);
     if (nvec <= 64) return SIRGCN_LAUNCH_VPL(2);

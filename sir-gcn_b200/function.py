@@ -105,7 +105,9 @@ EDGE_TIMERS = None
 
 
 def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da, e, out, de,
-               dst_scale, src_scale, da_scaled=None, accumulate=False):
+               dst_scale, src_scale, da_scaled=None, accumulate=False, e_index=None, de_partial=None):
+    """`e_index` (int32 per stored position): the edge term is row e_index[p] of the small TABLE `e` instead of row
+    eid[p] of an [E, d] tensor; `de_partial` (zeroed fp32 scratch): the dQ walk reduces that table's gradient."""
     if not (rows.indptr.is_cuda and q.is_cuda and k.is_cuda and out.is_cuda):
         raise RuntimeError("SIR-GCN edge kernels need CUDA tensors (no CPU fallback)")
     a = _lib.EdgeArgs()
@@ -114,7 +116,7 @@ def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da
     # an edgeless graph has an empty idx tensor (NULL data_ptr): hand the kernels any valid address,
     # it is never dereferenced because every row is empty
     a.indptr, a.idx = rows.indptr.data_ptr(), (rows.idx.data_ptr() or rows.indptr.data_ptr())
-    a.eid = None if rows.eid is None else rows.eid.data_ptr()
+    a.eid = e_index.data_ptr() if e_index is not None else (None if rows.eid is None else rows.eid.data_ptr())
     a.q, a.ldq = q.data_ptr(), _ld(q)
     a.k, a.ldk = k.data_ptr(), _ld(k)
     if da is not None:
@@ -134,6 +136,8 @@ def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da
     a.tile_row = None if rows.tile_row is None else rows.tile_row.data_ptr()
     a.n_tiles = rows.n_tiles
     a.accumulate = 1 if accumulate else 0
+    if de_partial is not None:
+        a.n_etypes, a.de_partial = e.shape[0], de_partial.data_ptr()
     dev = rows.indptr.device
     with torch.cuda.device(dev):
         if EDGE_TIMERS is not None:
@@ -146,7 +150,8 @@ def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da
     _lib.check(rc, fn_name)
 
 
-def edge_forward(csr: CompressedRows, q, k, e, dst_scale, src_scale, act, act_param, out=None, accumulate=False):
+def edge_forward(csr: CompressedRows, q, k, e, dst_scale, src_scale, act, act_param, out=None, accumulate=False,
+                 e_index=None):
     """A = fused edge stage over the rows of `csr` (q indexed by row, k by csr.idx); with `accumulate`,
     `out` (+)= the result — one walk per source block of a phased, partitioned forward."""
     d = q.shape[1]
@@ -154,31 +159,51 @@ def edge_forward(csr: CompressedRows, q, k, e, dst_scale, src_scale, act, act_pa
         out = _alloc_table(csr.n_rows, d, q.dtype, q.device)
     if csr.n_rows:
         _edge_call("sirgcn_edge_fwd", csr, d, q.dtype, act, act_param, q, k, None, e, out, None,
-                   dst_scale, src_scale, accumulate=accumulate)
+                   dst_scale, src_scale, accumulate=accumulate, e_index=e_index)
     out._sirgcn_padded = True
     return out
 
 
 def edge_backward_q(csr, q, k, e, da, dst_scale, src_scale, act, act_param, want_de, out=None,
-                    scale_da_inplace=False):
+                    scale_da_inplace=False, e_index=None):
     """dQ over the CSR (+ dE).  With `scale_da_inplace` (and a destination scale), the pass also overwrites
     dA[u] by dst_scale[u]·dA[u], so the CSC pass that follows can gather an already scaled table and needs
-    no per-edge scale lookup (pass it dst_scale=None)."""
+    no per-edge scale lookup (pass it dst_scale=None).  With `e_index` (edge term = rows of the small table `e`)
+    the returned dE is the TABLE's gradient, fp32 [n_types, d], reduced inside the walk: no [E, d] tensor."""
     d = q.shape[1]
     dq = _alloc_table(csr.n_rows, d, q.dtype, q.device) if out is None else out
+    scaled = da if (scale_da_inplace and dst_scale is not None) else None
+    if e_index is not None:
+        if not want_de:
+            if csr.n_rows:
+                _edge_call("sirgcn_edge_bwd_q", csr, d, q.dtype, act, act_param, q, k, da, e, dq, None,
+                           dst_scale, src_scale, scaled, e_index=e_index)
+            return dq, None
+        width = _pad_cols(d, q.dtype)
+        n_units = csr.n_tiles + csr.n_chunks
+        part = torch.zeros((max(n_units, 1), e.shape[0], width), dtype=torch.float32, device=q.device)
+        if csr.n_rows:
+            _edge_call("sirgcn_edge_bwd_q", csr, d, q.dtype, act, act_param, q, k, da, e, dq, None,
+                       dst_scale, src_scale, scaled, e_index=e_index, de_partial=part)
+        dtab = torch.empty((e.shape[0], d), dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            rc = _lib.lib().sirgcn_etable_grad(_lib.ptr(part), C.c_int64(n_units), C.c_int32(e.shape[0]), C.c_int32(width),
+                                               C.c_int32(d), _lib.ptr(dtab), C.c_int64(d), _lib.stream_ptr(q.device))
+        _lib.check(rc, "sirgcn_etable_grad")
+        return dq, dtab
     de = _alloc_table(e.shape[0], d, q.dtype, q.device) if (want_de and e is not None) else None
     if csr.n_rows:
         _edge_call("sirgcn_edge_bwd_q", csr, d, q.dtype, act, act_param, q, k, da, e, dq, de,
-                   dst_scale, src_scale, da if (scale_da_inplace and dst_scale is not None) else None)
+                   dst_scale, src_scale, scaled)
     return dq, de
 
 
-def edge_backward_k(csc, q, k, e, da, dst_scale, src_scale, act, act_param, out=None):
+def edge_backward_k(csc, q, k, e, da, dst_scale, src_scale, act, act_param, out=None, e_index=None):
     d = k.shape[1]
     dk = _alloc_table(csc.n_rows, d, k.dtype, k.device) if out is None else out
     if csc.n_rows:
         _edge_call("sirgcn_edge_bwd_k", csc, d, k.dtype, act, act_param, q, k, da, e, dk, None,
-                   dst_scale, src_scale)
+                   dst_scale, src_scale, e_index=e_index)
     return dk
 
 
@@ -229,9 +254,12 @@ class SIRLayerFunction(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, feat, w_qk, b_qk, e, w_r, b_r, graph, agg_type, act, act_param, d, recompute_qk=False,
-                keep_q=None, keep_k=None, drop_scale=1.0):
+                keep_q=None, keep_k=None, drop_scale=1.0, e_types=None):
         """keep_q / keep_k (torch.bool [N, d], or None): training-mode dropout of the two projections
-        (conv.py:60-61), applied in place on the halves of the [Q|K] buffer; backward masks dQ / dK the same way."""
+        (conv.py:60-61), applied in place on the halves of the [Q|K] buffer; backward masks dQ / dK the same way.
+        e_types (integer [E], or None): `e` is then a small TABLE [n_types, d] (the weight of an nn.Embedding edge
+        term, zinc/model.py:12-15) and the edge term of edge i is row e_types[i] of it, looked up inside the kernels;
+        the table's gradient is reduced inside the dQ walk.  No [E, d] tensor exists in either direction."""
         from . import gemm
         if not feat.is_cuda:
             raise RuntimeError("SIR-GCN kernels need CUDA tensors (no CPU fallback)")
@@ -246,8 +274,11 @@ class SIRLayerFunction(torch.autograd.Function):
             mask_scale_(q, keep_q, drop_scale)
         if e is not None:
             e = as_table(e.detach().to(qk.dtype))
+        ix_csr = ix_csc = None
+        if e_types is not None:
+            ix_csr, ix_csc = graph.edge_type_positions(e_types)
         ds, ss = graph.scales(agg_type)
-        a = edge_forward(graph.csr, q, k, e, ds, ss, act, act_param)
+        a = edge_forward(graph.csr, q, k, e, ds, ss, act, act_param, e_index=ix_csr)
         # recompute_qk: the [N, 2d] projection is not kept for backward but re-made from `feat` by one
         # more GEMM (≈5 % of the edge stage) — on the 50 M-node graph that is 25.6 GB per layer
         if recompute_qk:
@@ -284,6 +315,7 @@ class SIRLayerFunction(torch.autograd.Function):
         da = gemm.linear_dgrad(gout, w_r.to(qk.dtype), pad_to=_pad_cols(d, qk.dtype))[:, :d]   # [N, d]
         da._sirgcn_padded = True
         ds, ss = g.scales(ctx.agg_type)
+        ix_csr, ix_csc = ctx.e_index
         if ctx.lean:
             # memory-lean order for tables of many GB (the 50 M-node graph): dQ goes to a buffer of its own, dK is
             # written IN PLACE over K (the CSC walk reads K[v] only as the own operand of row v, before it stores
@@ -292,8 +324,8 @@ class SIRLayerFunction(torch.autograd.Function):
             # the peak for one extra 12.8 GB copy (≈ 4 ms of a 400 ms layer)
             dq_buf = _alloc_table(q.shape[0], d, qk.dtype, qk.device, zero=ldp != d)
             _, de = edge_backward_q(g.csr, q, k, e, da, ds, ss, ctx.act, ctx.act_param, need[3], out=dq_buf,
-                                    scale_da_inplace=True)
-            edge_backward_k(g.csc, q, k, e, da, None, ss, ctx.act, ctx.act_param, out=k)
+                                    scale_da_inplace=True, e_index=ix_csr)
+            edge_backward_k(g.csc, q, k, e, da, None, ss, ctx.act, ctx.act_param, out=k, e_index=ix_csc)
             del da
             ldq = _pad_cols(d, qk.dtype)                    # whole 16-byte vectors, zero padding included
             copy_rows(qk[:, :ldq], dq_buf.as_strided((dq_buf.shape[0], ldq), (dq_buf.stride(0), 1)))
@@ -304,8 +336,8 @@ class SIRLayerFunction(torch.autograd.Function):
             dq, dk = dqk[:, :d], dqk[:, ldp:ldp + d]
             # the dQ pass leaves dA scaled by the destination coefficient (in place: `da` is ours)
             _, de = edge_backward_q(g.csr, q, k, e, da, ds, ss, ctx.act, ctx.act_param, need[3], out=dq,
-                                    scale_da_inplace=True)
-            edge_backward_k(g.csc, q, k, e, da, None, ss, ctx.act, ctx.act_param, out=dk)
+                                    scale_da_inplace=True, e_index=ix_csr)
+            edge_backward_k(g.csc, q, k, e, da, None, ss, ctx.act, ctx.act_param, out=dk, e_index=ix_csc)
             del da
         del q, k, qk
         if keep_k is not None:                 # d(dropout): the same masks on the two gradient halves
@@ -316,7 +348,9 @@ class SIRLayerFunction(torch.autograd.Function):
         dw_qk = gemm.linear_wgrad(dqk, feat, w_qk.dtype) if need[1] else None
         db_qk = gemm.column_sum(dqk, w_qk.dtype) if (need[2] and ctx.has_bias[0]) else None
         dfeat = gemm.linear_dgrad(dqk, w_qk.to(dqk.dtype)).to(feat.dtype) if need[0] else None
-        return dfeat, dw_qk, db_qk, de, dw_r, db_r, None, None, None, None, None, None, None, None, None
+        if de is not None and ix_csr is not None:
+            de = de.to(w_qk.dtype)                  # the table's gradient, in the parameter's dtype
+        return dfeat, dw_qk, db_qk, de, dw_r, db_r, None, None, None, None, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------

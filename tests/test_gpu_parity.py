@@ -313,6 +313,83 @@ def test_sireconv_with_embedding_edge_term():
     run_layer(ref, gpu, src, dst, n, torch.randn(n, 16), bond)
 
 
+@pytest.mark.parametrize("agg", ["sum", "mean", "sym"])
+@pytest.mark.parametrize("act", ["relu", "leaky", "gelu"])
+@pytest.mark.parametrize("d,types", [(64, 4), (75, 7), (160, 8)])
+def test_embedding_edge_term_is_looked_up_in_kernel(agg, act, d, types):
+    """SURVEY K3 / zinc/model.py:12-15: with an nn.Embedding edge term the kernels index the TABLE by edge type and the
+    dQ walk reduces the table's gradient — the layer must never hand an [E, d] tensor to (or get one from) the edge
+    stage.  Hub rows exercise the chunk units; the table gradient must be bitwise repeatable."""
+    from sirgcn_b200 import function
+    n, e = 400, 5000
+    src, dst = rand_graph(n, e, 23, hub=4)
+    g = torch.Generator().manual_seed(9)
+    bond = torch.randint(0, types, (e,), generator=g)
+    ref, gpu = make_pair(RefSIREConv, SIREConv, 16, types, d, 24, ACTS[act](), agg_type=agg)
+    torch.manual_seed(1)
+    ref.linear_edge = nn.Embedding(types, d)
+    gpu.linear_edge = nn.Embedding(types, d).to(DEV)
+    gpu.load_state_dict(ref.state_dict())
+    seen = []
+    orig = function._edge_call
+
+    def spy(fn_name, rows, d_, dtype, act_, ap, q, k, da, e_, out, de, *a, **kw):
+        seen.append((fn_name, None if e_ is None else tuple(e_.shape), None if de is None else tuple(de.shape),
+                     kw.get("e_index") is not None, kw.get("de_partial") is not None))
+        return orig(fn_name, rows, d_, dtype, act_, ap, q, k, da, e_, out, de, *a, **kw)
+
+    function._edge_call = spy
+    try:
+        run_layer(ref, gpu, src, dst, n, torch.randn(n, 16), bond)
+    finally:
+        function._edge_call = orig
+    assert {s[0] for s in seen} == {"sirgcn_edge_fwd", "sirgcn_edge_bwd_q", "sirgcn_edge_bwd_k"}
+    for fn_name, e_shape, de_shape, indexed, partial in seen:
+        assert e_shape == (types, d) and de_shape is None and indexed, (fn_name, e_shape, de_shape)
+        assert partial == (fn_name == "sirgcn_edge_bwd_q")
+    # bitwise repeatable (fixed reduction order over lane groups and work units)
+    gg = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
+    x = torch.randn(n, 16, device=DEV)
+    grads = []
+    for _ in range(3):
+        gpu.zero_grad()
+        gpu(gg, x, bond.to(DEV)).sum().backward()
+        grads.append(gpu.linear_edge.weight.grad.clone())
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+
+
+def test_embedding_edge_term_16bit_and_constant_table():
+    n, e, d, types = 300, 4000, 128, 4
+    src, dst = rand_graph(n, e, 29, hub=2)
+    bond = torch.randint(0, types, (e,), generator=torch.Generator().manual_seed(2))
+    torch.manual_seed(0)
+    ref = RefSIREConv(32, types, d, 32, nn.GELU(), agg_type="mean")
+    ref.linear_edge = nn.Embedding(types, d)
+    gpu = SIREConv(32, types, d, 32, nn.GELU(), agg_type="mean")
+    gpu.linear_edge = nn.Embedding(types, d)
+    gpu.load_state_dict(ref.state_dict())
+    gpu = gpu.to(DEV).bfloat16()
+    ref.load_state_dict({k: v.bfloat16().float() for k, v in ref.state_dict().items()})
+    ref = ref.double()
+    ref.storage_dtype = torch.bfloat16
+    x = torch.randn(n, 32).bfloat16()
+    xr = x.double().requires_grad_(True)
+    out_r = ref(RefGraph(src, dst, n), xr, bond)
+    gout = torch.randn(n, 32).bfloat16()
+    gr = torch.autograd.grad(out_r, [xr, ref.linear_edge.weight], gout.double())
+    gg = Graph(src.to(DEV), dst.to(DEV), n, long_threshold=64)
+    xg = x.to(DEV).requires_grad_(True)
+    out_g = gpu(gg, xg, bond.to(DEV))
+    g_ = torch.autograd.grad(out_g, [xg, gpu.linear_edge.weight], gout.to(DEV))
+    assert rel_err(out_g, out_r) < LOWP_RTOL
+    assert rel_err(g_[0], gr[0]) < LOWP_RTOL and rel_err(g_[1], gr[1]) < LOWP_RTOL
+    # a frozen table (no gradient wanted): the dQ walk must not write any dE rows (a NULL dE table)
+    gpu.linear_edge.weight.requires_grad_(False)
+    out2 = gpu(gg, xg, bond.to(DEV))
+    (dx2,) = torch.autograd.grad(out2, [xg], gout.to(DEV))
+    assert torch.equal(dx2, g_[0])
+
+
 def test_generic_activation_and_inner_dims():
     """σ = Sequential(ReLU, Linear, ReLU) (synthetic-datasets/dictionary-lookup/model.py:17)."""
     n = 10
