@@ -267,9 +267,16 @@ def workload_config(args, w):
                f"layer l+1's K gathered in {args.chunks} destination chunks under layer l's walk, Q and dA gathers "
                f"under the other walks")
             + ("" if args.bwd_chunks <= 1 else f"; dK walk in {args.bwd_chunks} source chunks with the next dA table travelling under it")
+            + (f"; gathered tables chunk-major ({layout_chunks(args)} chunks: a chunk of all ranks lands in place, no staging copy)"
+               if layout_chunks(args) > 1 else "")
             + ("" if args.no_input_gather else "; node features of all ranks gathered ahead of the layers (layer 1 projects K/Q locally)"),
             "l2": "inputs >> 126 MB L2, no flush" if e * w["d"] * (4 if w["dtype"] == "f32" else 2) > (1 << 30)
             else "L2 flushed (256 MiB write) between timed steps"}
+
+
+def layout_chunks(args):
+    """gathered tables are laid out chunk-major with as many chunks as the cross-layer prefetch uses (partition.py)"""
+    return args.layout_chunks if args.layout_chunks > 0 else max(args.chunks, args.bwd_chunks, 1)
 
 
 def transport_name(args):
@@ -303,7 +310,7 @@ def partition_parity_check(args, w, layers, dev, rank, world):
     src, dst, _ = synth.powerlaw_hashed(n, e, alpha=2.3, max_deg=None, seed=3, device=dev)
     whole = Graph(src, dst, n, need_eid=False)
     part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, alpha=2.3, max_deg=None, seed=3, device=dev,
-                                                     transport=args.transport)
+                                                     transport=args.transport, layout_chunks=layout_chunks(args))
     gen = torch.Generator(device=dev)
     gen.manual_seed(99)                                   # the same features on every rank
     x = torch.randn((n, w["d_in"]), generator=gen, device=dev).to(dtype)
@@ -590,7 +597,8 @@ def run_gpu(args, w):
     else:
         from sirgcn_b200 import partition
         part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, alpha=2.3, max_deg=w["max_deg"],
-                                                         seed=0, device=dev, transport=args.transport)
+                                                         seed=0, device=dev, transport=args.transport,
+                                                         layout_chunks=layout_chunks(args))
         n_local, e_local = part.n_local, part.num_local_edges
         # the node features of ALL ranks, gathered ahead of the layers (an input: a prefetching loader gathers step
         # i+1's under step i); layer 1 then projects its K / Q tables locally instead of gathering both in line
@@ -825,6 +833,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunks", type=int, default=4,
                     help="N>1: destination chunks of the cross-layer K prefetch (1 = gather each K table whole)")
+    ap.add_argument("--layout-chunks", type=int, default=0,
+                    help="N>1: chunk-major layout of the gathered tables (0 = as many as --chunks; 1 = rank-major)")
     ap.add_argument("--bwd-chunks", type=int, default=1,
                     help="N>1: source chunks of the dK walk under which the layer below's dA table travels (1 = off)")
     ap.add_argument("--gather", default="projections", choices=["inputs", "projections"],

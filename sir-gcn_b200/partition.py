@@ -90,16 +90,24 @@ class CollectiveTransport:
         return sl.local.new_empty((self.part.world * sl.local.shape[0], sl.local.shape[1]))
 
     def gather(self, sl, full, lo=0, hi=None):
-        """rows [lo, hi) of every rank's slice -> full[r*rows + lo : r*rows + hi]; returns a handle"""
+        """rows [lo, hi) of every rank's slice -> their rows of the gathered table (RowPartition.table_row); returns a
+        handle.  A whole layout chunk of every rank lands in ONE contiguous block of the table, so it travels by
+        all_gather_into_tensor straight into place — no list of views, no staging copy."""
         part, rows = self.part, sl.local.shape[0]
         hi = rows if hi is None else hi
-        if part.world == 1:
+        G, step = part.world, part.step
+        if G == 1:
             full[lo:hi].copy_(sl.local[lo:hi])
             return _Handle([])
-        if lo == 0 and hi == rows:
-            return _Handle([dist.all_gather_into_tensor(full, sl.local, group=part.group, async_op=True)])
-        views = [full[r * rows + lo:r * rows + hi] for r in range(part.world)]
-        return _Handle([dist.all_gather(views, sl.local[lo:hi], group=part.group, async_op=True)])
+        works = []
+        for a, b, c in part.chunk_pieces(lo, hi):
+            if a == c * step and b == (c + 1) * step:
+                works.append(dist.all_gather_into_tensor(full[c * G * step:(c + 1) * G * step], sl.local[a:b],
+                                                         group=part.group, async_op=True))
+            else:       # part of a layout chunk: the ranks' pieces are not adjacent in the table
+                views = [full[part.table_row(r, a):part.table_row(r, a) + (b - a)] for r in range(G)]
+                works.append(dist.all_gather(views, sl.local[a:b], group=part.group, async_op=True))
+        return _Handle(works)
 
     def release(self, sl):
         pass
@@ -111,6 +119,7 @@ class PeerTransport:
 
     def __init__(self, part):
         from . import peer
+        self.part = part
         self.pool = peer.PeerPool(part.group)
 
     def acquire(self, rows, ld, dtype, device, zero):
@@ -124,7 +133,10 @@ class PeerTransport:
         return sl.local.new_empty((self.pool.world * sl.rows, sl.ld))
 
     def gather(self, sl, full, lo=0, hi=None):
-        return self.pool.gather(sl, full, lo, hi)
+        part = self.part
+        hs = [self.pool.gather(sl, full, a, b, dst_row_of=lambda r, a=a: part.table_row(r, a))
+              for a, b, _ in part.chunk_pieces(lo, sl.rows if hi is None else hi)]
+        return hs[0] if len(hs) == 1 else _Handle(hs)
 
     def release(self, sl):
         self.pool.release(sl)
@@ -141,6 +153,7 @@ class PushTransport:
 
     def __init__(self, part, mode):
         from . import peer
+        self.part = part
         self.pool = peer.PeerPool(part.group)
         self.mode = mode
         self.kind = {"ce": "push", "sm": "pushsm", "tma": "pushtma"}[mode]
@@ -156,7 +169,10 @@ class PushTransport:
         return pf.local
 
     def gather(self, sl, full, lo=0, hi=None):
-        return self.pool.push(sl.local, self._fulls[full.data_ptr()], lo, hi, self.mode)
+        part, pf = self.part, self._fulls[full.data_ptr()]
+        hs = [self.pool.push(sl.local, pf, a, b, self.mode, dst_row=part.table_row(part.rank, a))
+              for a, b, _ in part.chunk_pieces(lo, pf.rows if hi is None else hi)]
+        return hs[0] if len(hs) == 1 else _Handle(hs)
 
     def release(self, obj):
         if isinstance(obj, _FullToken):
@@ -188,26 +204,70 @@ class _Lease:
 class RowPartition:
     """Local slice of a graph for rank `rank` of `world` (see module docstring).
 
-    csr: rows = local destinations, idx = GLOBAL sources;  csc: rows = local sources, idx = GLOBAL destinations.
-    in_norm / out_norm / inv_in_deg: fp32 [G*n_pad] GLOBAL coefficient vectors (padding = 1)."""
+    csr: rows = local destinations, idx = sources;  csc: rows = local sources, idx = destinations — idx values are
+    ROWS OF THE GATHERED TABLES (table_row of the global node id), handed in as global ids and remapped here.
+    in_norm / out_norm / inv_in_deg: fp32 [G*n_pad] coefficient vectors in gathered-table order (padding = 1).
+
+    Gathered-table layout (`layout_chunks` = C): every rank's padded slice [n_pad = C*step rows] is cut into C chunks;
+    the table holds chunk 0 of rank 0..G-1, then chunk 1 of rank 0..G-1, ... — row (c*G + r)*step + j for local row
+    c*step + j of rank r.  Chunk c of ALL ranks is therefore one contiguous block that an all_gather_into_tensor
+    writes in place, which is what lets the cross-layer prefetch send a table chunk by chunk without staging copies
+    (C = 1 is the plain rank-major table, row = global node id)."""
 
     def __init__(self, num_nodes, rank, world, csr_local, csc_local, in_norm, out_norm, inv_in_deg, group=None,
-                 transport="auto"):
+                 transport="auto", layout_chunks=1):
         self.num_nodes_, self.rank, self.world, self.group = int(num_nodes), rank, world, group
         self._transport, self._transport_kind = None, transport
-        self.n_pad = (self.num_nodes_ + world - 1) // world
-        self.lo = min(self.num_nodes_, rank * self.n_pad)
-        self.hi = min(self.num_nodes_, self.lo + self.n_pad)
+        self.layout_chunks = max(1, int(layout_chunks))
+        self.n_pad, self.lo, self.hi = self.bounds(self.num_nodes_, rank, world, self.layout_chunks)
+        self.step = self.n_pad // self.layout_chunks
         self.csr, self.csc = csr_local, csc_local
+        n1 = max(self.hi - self.lo, 1)
+        # coefficients of the LOCAL rows (row side of the walks), taken before the table order is applied
+        self._local = {"in_norm": in_norm[self.lo:self.lo + n1].clone(), "out_norm": out_norm[self.lo:self.lo + n1].clone(),
+                       "inv_in_deg": inv_in_deg[self.lo:self.lo + n1].clone()}
+        if self.layout_chunks > 1 and world > 1:
+            reorder = lambda v: v.view(world, self.layout_chunks, self.step).transpose(0, 1).reshape(-1).contiguous()
+            in_norm, out_norm, inv_in_deg = reorder(in_norm), reorder(out_norm), reorder(inv_in_deg)
+            self._remap_(self.csr.idx)
+            self._remap_(self.csc.idx)
         self.in_norm, self.out_norm, self.inv_in_deg = in_norm, out_norm, inv_in_deg
         self.num_local_edges = csr_local.num_pos
         self._row_chunks = {}
 
     @staticmethod
-    def bounds(num_nodes, rank, world):
-        n_pad = (num_nodes + world - 1) // world
+    def bounds(num_nodes, rank, world, layout_chunks=1):
+        """(n_pad, lo, hi): rows per padded slice (a multiple of layout_chunks) and this rank's global row range"""
+        c = max(1, int(layout_chunks))
+        n_pad = ((num_nodes + world - 1) // world + c - 1) // c * c
         lo = min(num_nodes, rank * n_pad)
         return n_pad, lo, min(num_nodes, lo + n_pad)
+
+    # ---- gathered-table layout -------------------------------------------------------------------------------
+    def table_row(self, r, i):
+        """row of the gathered tables that holds local row i of rank r"""
+        c = i // self.step
+        return (c * self.world + r) * self.step + (i - c * self.step)
+
+    def chunk_pieces(self, lo, hi):
+        """[(a, b, c)]: the local row range [lo, hi) cut at layout-chunk boundaries (piece [a, b) lies in chunk c)"""
+        out, a = [], lo
+        while a < hi:
+            c = a // self.step
+            b = min(hi, (c + 1) * self.step)
+            out.append((a, b, c))
+            a = b
+        return out
+
+    def _remap_(self, idx, block=1 << 26):
+        """global node ids -> gathered-table rows, in place (bounded temporaries: the 2 B-edge graph has 250 M per rank)"""
+        G, n_pad, step = self.world, self.n_pad, self.step
+        for a in range(0, idx.numel(), block):
+            g = idx[a:a + block]
+            r = torch.div(g, n_pad, rounding_mode="floor")
+            i = g - r * n_pad
+            c = torch.div(i, step, rounding_mode="floor")
+            g.copy_((c * G + r) * step + (i - c * step))
 
     @property
     def n_local(self):
@@ -219,7 +279,7 @@ class RowPartition:
         covers rows [lo, min(hi, n_local)) and is None when that range is empty."""
         got = self._row_chunks.get(chunks)
         if got is None:
-            step = (self.n_pad + chunks - 1) // chunks
+            step = self._cut_step(chunks)
             got = []
             for c in range(chunks):
                 lo, hi = min(self.n_pad, c * step), min(self.n_pad, (c + 1) * step)
@@ -230,11 +290,18 @@ class RowPartition:
             self._row_chunks[chunks] = got
         return got
 
+    def _cut_step(self, chunks):
+        """rows per cut of the walks: whole layout chunks when the table is chunk-major (cuts then coincide with the
+        contiguous blocks of the gathered tables)"""
+        if self.layout_chunks > 1 and self.layout_chunks % chunks == 0:
+            return self.step * (self.layout_chunks // chunks)
+        return (self.n_pad + chunks - 1) // chunks
+
     def col_chunks(self, chunks):
         """the same cut of the local SOURCE rows (out-CSC), for the chunked dK walk of the backward pass"""
         got = self._row_chunks.get(("csc", chunks))
         if got is None:
-            step = (self.n_pad + chunks - 1) // chunks
+            step = self._cut_step(chunks)
             got = []
             for c in range(chunks):
                 lo, hi = min(self.n_pad, c * step), min(self.n_pad, (c + 1) * step)
@@ -248,33 +315,33 @@ class RowPartition:
     # ---- construction ---------------------------------------------------------------------------------
     @classmethod
     def from_csr_csc(cls, csr: CompressedRows, csc: CompressedRows, num_nodes, rank, world, group=None,
-                     in_norm=None, out_norm=None, inv_in_deg=None, transport="auto"):
+                     in_norm=None, out_norm=None, inv_in_deg=None, transport="auto", layout_chunks=1):
         """slice replicated whole-graph structures (tests, small graphs)"""
         n = int(num_nodes)
-        n_pad, lo, hi = cls.bounds(n, rank, world)
+        n_pad, lo, hi = cls.bounds(n, rank, world, layout_chunks)
         if in_norm is None:
             in_deg = (csr.indptr[1:] - csr.indptr[:-1]).clamp(min=1).to(torch.float32)
             out_deg = (csc.indptr[1:] - csc.indptr[:-1]).clamp(min=1).to(torch.float32)
             in_norm, out_norm, inv_in_deg = 1.0 / torch.sqrt(in_deg), 1.0 / torch.sqrt(out_deg), 1.0 / in_deg
         pad = lambda t: torch.cat([t, t.new_ones(world * n_pad - n)]) if world * n_pad > n else t
         return cls(n, rank, world, csr.slice_rows(lo, hi), csc.slice_rows(lo, hi),
-                   pad(in_norm), pad(out_norm), pad(inv_in_deg), group, transport)
+                   pad(in_norm), pad(out_norm), pad(inv_in_deg), group, transport, layout_chunks)
 
     @classmethod
-    def from_graph(cls, graph: Graph, rank, world, group=None, transport="auto"):
+    def from_graph(cls, graph: Graph, rank, world, group=None, transport="auto", layout_chunks=1):
         """slice an already converted (replicated) Graph; the caller may drop `graph` afterwards"""
         return cls.from_csr_csc(graph.csr, graph.csc, graph.num_nodes(), rank, world, group,
-                                graph.in_norm, graph.out_norm, graph.inv_in_deg, transport)
+                                graph.in_norm, graph.out_norm, graph.inv_in_deg, transport, layout_chunks)
 
     @classmethod
     def from_local_edges(cls, num_nodes, rank, world, in_src, in_dst, out_src, out_dst, group=None,
-                         long_threshold=DEFAULT_LONG_THRESHOLD, in_indptr=None, transport="auto"):
+                         long_threshold=DEFAULT_LONG_THRESHOLD, in_indptr=None, transport="auto", layout_chunks=1):
         """build from this rank's two edge lists (GLOBAL ids): the edges whose destination is local
         (in_src -> in_dst) and the edges whose source is local (out_src -> out_dst).  When the first list is
         already destination-sorted, pass its local row pointer `in_indptr` instead of `in_dst`.  Degree
         coefficients of the whole graph are assembled with one all_gather each."""
         n = int(num_nodes)
-        n_pad, lo, hi = cls.bounds(n, rank, world)
+        n_pad, lo, hi = cls.bounds(n, rank, world, layout_chunks)
         dev = in_src.device
         nl = hi - lo
         if in_indptr is not None:
@@ -296,38 +363,35 @@ class RowPartition:
                 full.copy_(buf)
             return full
         return cls(n, rank, world, csr, csc, gather(1.0 / torch.sqrt(in_deg)), gather(1.0 / torch.sqrt(out_deg)),
-                   gather(1.0 / in_deg), group, transport)
+                   gather(1.0 / in_deg), group, transport, layout_chunks)
 
     @classmethod
     def synthetic_powerlaw(cls, num_nodes, num_edges, rank, world, alpha=2.3, max_deg=None, seed=0, device="cuda",
-                           group=None, long_threshold=DEFAULT_LONG_THRESHOLD, transport="auto"):
+                           group=None, long_threshold=DEFAULT_LONG_THRESHOLD, transport="auto", layout_chunks=1):
         """this rank's slice of synth.powerlaw_hashed (the SAME global graph on every world size), generated on
         the device without any edge exchange"""
         from . import synth
         indptr = synth.powerlaw_indptr(num_nodes, num_edges, alpha, max_deg, seed, device)
-        n_pad, lo, hi = cls.bounds(num_nodes, rank, world)
+        n_pad, lo, hi = cls.bounds(num_nodes, rank, world, layout_chunks)
         in_src, _ = synth.powerlaw_hashed_rows(indptr, num_nodes, lo, hi, seed, want_dst=False)
         out_src, out_dst = synth.powerlaw_hashed_cols(indptr, num_nodes, lo, hi, seed)
         in_indptr = indptr[lo:hi + 1] - indptr[lo]
         del indptr
         return cls.from_local_edges(num_nodes, rank, world, in_src, None, out_src, out_dst, group, long_threshold,
-                                    in_indptr=in_indptr, transport=transport)
+                                    in_indptr=in_indptr, transport=transport, layout_chunks=layout_chunks)
 
     # ---- coefficients --------------------------------------------------------------------------------------
-    def _rows(self, v):
-        return v[self.lo:self.lo + max(self.n_local, 1)]
-
     def scales_rows(self, agg_type):
         """(dst_scale, src_scale) for the CSR walks: dst = local row, src = row of the gathered K table"""
         if agg_type == "sym":
-            return self._rows(self.in_norm), self.out_norm
+            return self._local["in_norm"], self.out_norm
         if agg_type == "mean":
-            return self._rows(self.inv_in_deg), None
+            return self._local["inv_in_deg"], None
         return None, None
 
     def scale_cols_rows(self, agg_type):
         """row (= local source) scale of the CSC walk; its destination scale is folded into dA before the gather"""
-        return self._rows(self.out_norm) if agg_type == "sym" else None
+        return self._local["out_norm"] if agg_type == "sym" else None
 
     # ---- transport --------------------------------------------------------------------------------------------
     def transport(self):
@@ -369,8 +433,13 @@ class RowPartition:
             src[:local.shape[0]].copy_(local)
         if self.world == 1:
             full.copy_(src)
-        else:
+        elif self.layout_chunks == 1:
             dist.all_gather_into_tensor(full, src.contiguous(), group=self.group)
+        else:           # gathered-table order: chunk c of every rank is one contiguous block
+            src, G, step = src.contiguous(), self.world, self.step
+            for c in range(self.layout_chunks):
+                dist.all_gather_into_tensor(full[c * G * step:(c + 1) * G * step], src[c * step:(c + 1) * step],
+                                            group=self.group)
         return full
 
     def all_reduce_(self, t):
@@ -454,10 +523,34 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                 for hnd in h_handles:
                     hnd.wait()
                 _mark("fwd:wait_H")
-                k_all = torch.empty((h_full.shape[0], ld), dtype=dt, device=dev) if ld == d else \
-                    torch.zeros((h_full.shape[0], ld), dtype=dt, device=dev)
-                _project(h_full.to(dt), w_k.to(dt), None, k_all, h_full.shape[0], d, ld)
-                k_sl = _CollectiveSlice(k_all[part.rank * part.n_pad:(part.rank + 1) * part.n_pad])
+                rows_all = h_full.shape[0]
+                keep = opts.get("keep_q_full")
+                if keep is None:    # auto: ONE [Q|K] GEMM over the gathered input, Q kept for the backward CSC walk,
+                    # when the extra table fits comfortably (8 GPUs: yes; 2 GPUs on the 2 B-edge graph: no)
+                    keep = train and (not h_full.is_cuda or
+                                      torch.cuda.mem_get_info(dev)[0] > 4 * rows_all * ld * h_full.element_size())
+                q_all_kept = None
+                if keep and train:
+                    w_cat_f = (torch.zeros if ld != d else torch.empty)((2 * ld, w_q.shape[1]), dtype=dt, device=dev)
+                    w_cat_f[:d].copy_(w_q)
+                    w_cat_f[ld:ld + d].copy_(w_k)
+                    b_cat_f = None
+                    if b_q is not None:
+                        b_cat_f = torch.zeros(2 * ld, dtype=dt, device=dev)
+                        b_cat_f[:d].copy_(b_q)
+                    qk_all = gemm.linear_forward(h_full.to(dt), w_cat_f, b_cat_f)       # [rows_all, 2·ld]
+                    k_all = qk_all[:, ld:2 * ld]            # row stride 2·ld: the walks take any 16-byte row pitch
+                    q_all_kept = qk_all[:, :ld]
+                    del qk_all
+                else:
+                    k_all = torch.empty((rows_all, ld), dtype=dt, device=dev) if ld == d else \
+                        torch.zeros((rows_all, ld), dtype=dt, device=dev)
+                    _project(h_full.to(dt), w_k.to(dt), None, k_all, rows_all, d, ld)
+                # this rank's own K rows (row operand and output of the backward CSC walk): projected from the local
+                # input — in a chunk-major table they are not one contiguous slice of k_all
+                k_sl = _CollectiveSlice((torch.zeros if ld != d else torch.empty)((part.n_pad, ld), dtype=dt, device=dev))
+                if train:
+                    _project(h, w_k.to(dt), None, k_sl.local, n, d, ld)
                 k_handles = []
             elif pre is None:
                 k_sl = lease.add(tr.acquire(part.n_pad, ld, dt, dev, zero=ld != d))
@@ -539,7 +632,9 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             # as layer l is done — the whole stack is ONE autograd node, whose saved tensors would otherwise all live
             # until its backward returns (at 2 GPUs that is the difference between fitting the 2 B-edge graph or not)
             state.append(dict(k_sl=k_sl, q_sl=q_sl, q_full=q_full, q_h=q_h, d=d, ld=ld, k_all=k_all, a=a,
-                              h=None if l == 0 else h, h_full=None if l == 0 else h_full, has_full=h_full is not None))
+                              h=None if l == 0 else h, h_full=None if l == 0 else h_full, has_full=h_full is not None,
+                              q_all_kept=q_all_kept if h_full is not None else None))
+            q_all_kept = None
             h, h_full, h_handles = out, h_full_next, h_handles_next
         if not train:
             for lease in leases:
@@ -606,7 +701,10 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             _mark("bwd:dA")
             be.backward_q(part.csr, q, kf, None, da, None, ss, act, act_param, False, out=dq)
             _mark("bwd:edge_q")
-            if h_full is not None:
+            if h_full is not None and st["q_all_kept"] is not None:
+                st["q_full"] = st["q_all_kept"]             # made by the forward pass's one [Q|K] GEMM over the input
+                st["q_all_kept"] = None
+            elif h_full is not None:
                 # the Q table of ALL destinations is a projection of the layer input that every rank holds: made here
                 qf_buf = (torch.empty if ld == d else torch.zeros)((h_full.shape[0], ld), dtype=dt, device=dev)
                 _project(h_full.to(dt), w_q.to(dt), b_q, qf_buf, h_full.shape[0], d, ld)
@@ -667,7 +765,7 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                     g = gemm.linear_dgrad(dqk, w_cat)
             _mark("bwd:edge_k")
             del da_full, daf, qf, kf, k_all, q, k, da, a, dq, dk, da_sl, q_sl, k_sl, da_handles, h_full
-            for key in ("q_full", "q_h", "k_all", "a", "k_sl", "q_sl", "h_full"):
+            for key in ("q_full", "q_h", "k_all", "a", "k_sl", "q_sl", "h_full", "q_all_kept"):
                 st[key] = None
             featd = feat.to(dt)
             if wneed[l][0] or wneed[l][2]:
@@ -707,7 +805,7 @@ def _layer_args(layer):
 
 
 def partitioned_sirconv_stack(layers, part: RowPartition, feat_loc, chunks=4, backend=CudaEdgeBackend,
-                              feat_full=None, gather="projections", bwd_chunks=1):
+                              feat_full=None, gather="projections", bwd_chunks=1, keep_q_full=None):
     """Run consecutive `SIRConv` layers (output of one = input of the next, nothing in between) on this rank's rows
     of a partitioned graph as one autograd node; `chunks` = destination chunks of the cross-layer prefetch.
     `feat_loc` = rows [part.lo, part.hi) of the node features; `feat_full` (optional) = the rows of all ranks,
@@ -718,7 +816,9 @@ def partitioned_sirconv_stack(layers, part: RowPartition, feat_loc, chunks=4, ba
     limit).
     `bwd_chunks` > 1: the dK walk of every layer but the first runs in that many source chunks, and chunk c of the
     layer below's dA table (dH[c]·W_R, scaled) travels under the walk of chunk c+1 — the layer below then starts its
-    dQ walk with no transfer competing for the SMs and its dA table already in place."""
+    dQ walk with no transfer competing for the SMs and its dA table already in place.
+    `keep_q_full` (with feat_full / gather="inputs"): a layer whose gathered input is at hand makes its K AND Q tables
+    of all ranks by ONE [Q|K] GEMM in forward and keeps Q for the backward CSC walk (None = when memory allows)."""
     if gather not in ("inputs", "projections"):
         raise ValueError(f"gather must be 'inputs' or 'projections', not {gather!r}")
     if feat_loc.shape[0] != part.n_local:
@@ -732,7 +832,7 @@ def partitioned_sirconv_stack(layers, part: RowPartition, feat_loc, chunks=4, ba
         c, w = _layer_args(layer)
         cfgs.append(c)
         weights += list(w)
-    opts = {"chunks": chunks, "gather": gather, "bwd_chunks": bwd_chunks}
+    opts = {"chunks": chunks, "gather": gather, "bwd_chunks": bwd_chunks, "keep_q_full": keep_q_full}
     return PartitionedSIRStackFunction.apply(feat_loc, part, tuple(cfgs), opts, backend, feat_full, *weights)
 
 

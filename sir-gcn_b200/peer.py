@@ -251,13 +251,16 @@ class PeerPool:
         sl.waited_at = -1
 
     # ---- the all-gather -----------------------------------------------------------------------------------------
-    def gather(self, sl: PeerSlice, full, lo=0, hi=None):
-        """rows [lo, hi) of every rank's slice -> full[r*rows + lo : r*rows + hi] (full is [world*rows, ld]).  The pulls
+    def gather(self, sl: PeerSlice, full, lo=0, hi=None, dst_row_of=None):
+        """rows [lo, hi) of every rank's slice -> full[dst_row_of(r) : + hi - lo] (full is [world*rows, ld];
+        dst_row_of(r) = r*rows + lo unless the caller lays the table out differently, partition.table_row).  The pulls
         run on the pool's copy streams behind a barrier ("every rank has written these rows") that does not block
         the current stream; the own rows are copied on the current stream.  Returns a PullHandle."""
         hi = sl.rows if hi is None else hi
+        if dst_row_of is None:
+            dst_row_of = lambda r: r * sl.rows + lo
         if self.world == 1:
-            full[lo:hi].copy_(sl.local[lo:hi])
+            full[dst_row_of(0):dst_row_of(0) + hi - lo].copy_(sl.local[lo:hi])
             return PullHandle(self, sl, None, self.barriers)
         index, done = self.barrier(blocking=False)
         events = []
@@ -266,7 +269,7 @@ class PeerPool:
             peer = (self.rank + i) % self.world             # staggered: at any moment the ranks read different peers
             st = self.streams[i - 1]
             st.wait_event(done)
-            dst = full.data_ptr() + peer * sl.rows * sl.row_bytes + off
+            dst = full.data_ptr() + dst_row_of(peer) * sl.row_bytes
             with torch.cuda.device(self.device):
                 rc = self.lib.sirgcn_peer_copy(C.c_void_p(dst), C.c_void_p(sl.peer_ptr[peer] + off), C.c_size_t(nbytes),
                                                C.c_void_p(st.cuda_stream))
@@ -274,7 +277,7 @@ class PeerPool:
             ev = torch.cuda.Event()
             ev.record(st)
             events.append(ev)
-        full[self.rank * sl.rows + lo:self.rank * sl.rows + hi].copy_(sl.local[lo:hi])
+        full[dst_row_of(self.rank):dst_row_of(self.rank) + hi - lo].copy_(sl.local[lo:hi])
         h = PullHandle(self, sl, events, index)
         sl.pending.append(h)
         sl.gathered = True
@@ -301,7 +304,7 @@ class PeerPool:
         pf.released_at = self.barriers
         self.free_full.setdefault((pf.rows, pf.ld, pf.dtype), []).append(pf)
 
-    def push(self, src, pf: PeerFull, lo=0, hi=None, mode="ce"):
+    def push(self, src, pf: PeerFull, lo=0, hi=None, mode="ce", dst_row=None):
         """rows [lo, hi) of this rank's slice `src` ([rows, ld], any local tensor that stays alive until the handle has
         been waited for) -> rows rank*rows + lo.. of EVERY rank's table.  mode "ce": one copy-engine write per peer;
         "sm": one fan-out kernel of a few CTAs (sirgcn_peer_push); "tma": the same with TMA bulk copies issued by one
@@ -310,9 +313,11 @@ class PeerPool:
         landed".  Returns a PushHandle."""
         hi = pf.rows if hi is None else hi
         cur = torch.cuda.current_stream(self.device)
-        mine = self.rank * pf.rows
+        # row of the gathered table where src[lo] goes (the same in every rank's table): rank-major unless the caller
+        # lays the table out differently (partition.table_row)
+        mine = self.rank * pf.rows if dst_row is None else dst_row - lo
         if self.world == 1:
-            pf.local[lo:hi].copy_(src[lo:hi])
+            pf.local[mine + lo:mine + hi].copy_(src[lo:hi])
             return PushHandle(self, None, self.barriers)
         # "every rank is done reading the table's previous contents": always a barrier of its own.  Skipping it when
         # one has been issued since release_full() would make the barrier COUNT depend on when the lease was released

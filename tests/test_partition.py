@@ -108,7 +108,7 @@ def _reference(src, dst, n, layer, x, gout):
     return out.detach(), grads
 
 
-def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, gather, bwd_chunks, ret):
+def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, gather, bwd_chunks, ret, layout=1, keep_q=None):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -120,8 +120,9 @@ def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, gather
         c = csr_csc_ref(src, dst, n)
         csr = CompressedRows(c[0], c[1], None)
         csc = CompressedRows(c[3], c[4], None)
-        part = partition.RowPartition.from_csr_csc(csr, csc, n, rank, world)
+        part = partition.RowPartition.from_csr_csc(csr, csc, n, rank, world, layout_chunks=layout)
         assert part.transport().kind == "collective"
+        assert part.n_pad % layout == 0 and part.n_pad * world >= n
         cuts = part.row_chunks(chunks)
         assert len(cuts) == chunks and cuts[0][0] == 0 and cuts[-1][1] == part.n_pad
         assert sum(r.num_pos for _, _, r in cuts if r is not None) == part.csr.num_pos
@@ -133,9 +134,14 @@ def _gloo_worker(rank, world, port, agg, act, n_layers, chunks, use_full, gather
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
         x_full = part.all_gather_rows(xl.detach()) if use_full else None
         if use_full:
-            assert x_full.shape[0] == world * part.n_pad and torch.equal(x_full[:n], x)
+            assert x_full.shape[0] == world * part.n_pad
+            rows = torch.tensor([part.table_row(g // part.n_pad, g % part.n_pad) for g in range(n)])
+            assert torch.equal(x_full[rows], x)         # gathered-table order (rank-major when layout == 1)
+            if layout == 1:
+                assert torch.equal(x_full[:n], x)
         out = partition.partitioned_sirconv_stack(layers, part, xl, chunks=chunks, backend=TorchEdgeBackend,
-                                                  feat_full=x_full, gather=gather, bwd_chunks=bwd_chunks)
+                                                  feat_full=x_full, gather=gather, bwd_chunks=bwd_chunks,
+                                                  keep_q_full=keep_q)
         grads = torch.autograd.grad(out, [xl] + [p for l in layers for p in l.parameters()], gout[part.lo:part.hi])
         # degree coefficients are fp32 by design (the kernels read fp32 scales): 1e-6; pure sums: 1e-10
         tol = dict(rtol=1e-10, atol=1e-12) if agg == "sum" else dict(rtol=1e-6, atol=1e-7)
@@ -168,13 +174,26 @@ def test_partition_gloo_world3_ragged_last_rank(agg, act, n_layers, chunks, use_
     _run_gloo(3, agg, act, n_layers, chunks, use_full, gather, bwd_chunks)
 
 
-def _run_gloo(world, agg, act, n_layers, chunks, use_full, gather, bwd_chunks):
+def _run_gloo(world, agg, act, n_layers, chunks, use_full, gather, bwd_chunks, layout=1, keep_q=None):
     port = _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_gloo_worker, args=(world, port, agg, act, n_layers, chunks, use_full, gather, bwd_chunks, ret),
-                 nprocs=world, join=True)
+        mp.spawn(_gloo_worker, args=(world, port, agg, act, n_layers, chunks, use_full, gather, bwd_chunks, ret, layout,
+                                     keep_q), nprocs=world, join=True)
         assert dict(ret) == {r: True for r in range(world)}
+
+
+@pytest.mark.parametrize("world,agg,act,n_layers,chunks,use_full,gather,bwd_chunks,layout,keep_q", [
+    (2, "mean", "relu", 2, 4, True, "projections", 4, 4, None),     # the bench's schedule: cuts == layout chunks
+    (2, "sym", "leaky", 2, 2, True, "projections", 1, 4, False),    # cuts of two layout chunks each
+    (2, "sym", "gelu", 3, 4, False, "projections", 2, 4, None),     # no gathered input: K and Q travel
+    (2, "mean", "leaky", 2, 3, True, "inputs", 3, 4, None),         # cuts that split layout chunks (partial pieces)
+    (3, "sym", "relu", 2, 8, True, "projections", 8, 8, None),      # ragged last rank, empty chunks
+    (3, "sum", "gelu", 2, 2, False, "inputs", 1, 2, True)])
+def test_partition_gloo_chunk_major_tables(world, agg, act, n_layers, chunks, use_full, gather, bwd_chunks, layout, keep_q):
+    """gathered tables laid out chunk-major (RowPartition.layout_chunks): index remap, permuted coefficient vectors,
+    in-place chunk all-gathers, the one-GEMM [Q|K] projection of a gathered input kept for backward"""
+    _run_gloo(world, agg, act, n_layers, chunks, use_full, gather, bwd_chunks, layout, keep_q)
 
 
 @pytest.mark.parametrize("n_layers,gather,bwd_chunks,use_full", [(1, "projections", 1, False), (2, "projections", 1, True),
@@ -263,7 +282,7 @@ def test_partition_from_hashed_generator_matches_whole_graph_slices():
         assert torch.equal(csc.indptr, whole.csc.indptr) and torch.equal(csc.idx, whole.csc.idx)
 
 
-def _nccl_worker(rank, world, port, transport, chunks, barrier, ret):
+def _nccl_worker(rank, world, port, transport, chunks, barrier, ret, layout=1):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     os.environ["SIRGCN_TRANSPORT"], os.environ["SIRGCN_PEER_BARRIER"] = transport, barrier
     torch.cuda.set_device(rank)
@@ -272,7 +291,8 @@ def _nccl_worker(rank, world, port, transport, chunks, barrier, ret):
     try:
         from sirgcn_b200 import synth
         n, e, d = 20011, 600000, 128
-        part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, seed=3, device=dev, long_threshold=64)
+        part = partition.RowPartition.synthetic_powerlaw(n, e, rank, world, seed=3, device=dev, long_threshold=64,
+                                                         layout_chunks=layout)
         assert part.transport().kind == transport
         # same device as the partition: the degree law is drawn with the device's RNG
         src, dst, _ = synth.powerlaw_hashed(n, e, seed=3, device=dev, index_dtype=torch.int64)
@@ -324,16 +344,18 @@ def _nccl_worker(rank, world, port, transport, chunks, barrier, ret):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("transport,chunks,barrier", [("collective", 3, "flags"), ("peer", 4, "flags"),
-                                                      ("peer", 1, "nccl"), ("push", 4, "flags"),
-                                                      ("pushsm", 3, "flags")])
-def test_partition_nccl_world2(transport, chunks, barrier):
+@pytest.mark.parametrize("transport,chunks,barrier,layout", [
+    ("collective", 3, "flags", 1), ("peer", 4, "flags", 1), ("peer", 1, "nccl", 1), ("push", 4, "flags", 1),
+    ("pushsm", 3, "flags", 1), ("pushtma", 4, "flags", 1),
+    ("collective", 4, "flags", 4), ("push", 4, "flags", 4), ("pushsm", 2, "flags", 4), ("pushtma", 4, "flags", 4),
+    ("peer", 4, "flags", 4)])
+def test_partition_nccl_world2(transport, chunks, barrier, layout):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     world, port = 2, _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_nccl_worker, args=(world, port, transport, chunks, barrier, ret), nprocs=world, join=True)
+        mp.spawn(_nccl_worker, args=(world, port, transport, chunks, barrier, ret, layout), nprocs=world, join=True)
         assert len(ret) == 2 and max(max(v) for v in ret.values()) < 1e-5, dict(ret)
 
 
