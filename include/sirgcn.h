@@ -235,6 +235,17 @@ int sirgcn_colsum(const void *x, int64_t ld, int64_t m, int32_t n, int32_t dtype
 int sirgcn_copy_rows(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
                      int64_t row_bytes, int64_t rows, void *stream);
 
+/* Weight and bias gradients of a projection on the tcgen05 tensor cores (16-bit tables, fp32 accumulation in TMEM):
+ *     dW[n_out, k_in] = dY[m, n_out]^T · X[m, k_in]      db[n_out] = column sums of dY   (db may be NULL)
+ * — the autograd backward of nn.Linear behind conv.py:60-61,:65.  Both tables are read once, as
+ * stored (MN-major MMA operands fed by TMA: no transpose); the node dimension is split over the SMs and the fp32
+ * partials of the splits are summed in split order (bitwise repeatable).  dW / db are fp32.  n_out, k_in, ldy, ldx
+ * multiples of 8; workspace: sirgcn_gemm_wgrad_workspace_bytes(m, n_out, k_in) bytes of device scratch. */
+size_t sirgcn_gemm_wgrad_workspace_bytes(int64_t m, int32_t n_out, int32_t k_in);
+int sirgcn_gemm_wgrad(const void *dy, int64_t ldy, const void *x, int64_t ldx, int64_t m, int32_t n_out, int32_t k_in,
+                      int32_t dtype, float *dw, int64_t ld_dw, float *db, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
 /* Dropout applied in place on a row table (the K / Q halves of the [N, 2·ld] projection buffer and, in backward, the
  * dK / dQ halves): table[r, c] = keep[r*d + c] ? table[r, c] * scale : 0 (fp32 product, rounded once — ATen's fused
  * dropout arithmetic), columns d..pad are zeroed.  keep = dense [rows, d] bytes (0 / 1), drawn by the host with

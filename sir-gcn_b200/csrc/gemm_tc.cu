@@ -16,9 +16,7 @@
 //            two TMEM accumulator stages let tile i+1's MMAs overlap tile i's epilogue
 // These GEMMs are skinny (K = d_in <= 512, N = 2d or d_out): they sit at the memory/compute ridge
 // (DESIGN.md §2.4), so the tile is chosen to read A once and write C once; B is L2-resident.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sirgcn {
 namespace {
@@ -34,70 +32,6 @@ constexpr int kGemmThreads = 192;
 constexpr int kCBoxBytes = kBM * 64 * 2;      // one 128 x 64 output box (128-byte swizzled rows) = 16 KB
 constexpr int kCBytes = (kMaxBN / 64) * kCBoxBytes;   // output staging for the TMA store: 64 KB
 constexpr int kSmemBytes = kStages * kStageBytes + kCBytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment slack*/;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int x, int y) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major operand tile written by TMA with CU_TENSOR_MAP_SWIZZLE_128B: rows of 128 bytes, 8-row groups of 1024 B
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);         // start address            bits [0,14)
-    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: next 8-row group
-    d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                          // layout type: SWIZZLE_128B
-    return d;
-}
 
 // instruction descriptor for kind::f16: D = fp32, A/B = bf16 or fp16, both K-major, M = 128, N = bn
 __device__ __forceinline__ uint32_t umma_idesc(int bn, bool bf16) {
@@ -271,44 +205,232 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
+// =====================================================================================================================
+// fp32 tables: C[M, N] = A[M, K] · B[N, K]^T (+ bias) in fp32 on the tensor cores by the 3xTF32 split
+//     a = a_hi + a_lo,  a_hi = a rounded to TF32 (10 explicit mantissa bits), a_lo = a - a_hi (exact in fp32)
+//     a·b ≈ a_hi·b_hi + a_lo·b_hi + a_hi·b_lo            (the dropped a_lo·b_lo is 2^-22 relative)
+// fp32 accumulation in TMEM; measured ~1e-6 relative against fp64, inside the 1e-5 fp32 parity target that plain TF32
+// (1e-3) misses and that made round 1 keep the library SGEMM (tcgen05 has no IEEE fp32 MMA).  The reference computes
+// these projections with cuBLAS SGEMM (/root/reference/models/conv.py:60-61,:65).
+// Same structure as gemm_tn_kernel plus a SPLITTER warpgroup: TMA lands the raw fp32 tiles (128-byte swizzled rows of
+// 32 floats); warps 6-9 rewrite each tile in place as its hi part and write the lo part to a twin tile at the same
+// offsets (an elementwise rewrite keeps the swizzle), fence to the async proxy and hand the stage to the MMA warp,
+// which issues three kind::tf32 MMAs per 8-wide K step.
+// =====================================================================================================================
+constexpr int kF32BK = 32;                          // fp32 elements per 128-byte swizzle row
+constexpr int kF32MaxBN = 128;
+constexpr int kF32Stages = 2;
+constexpr int kF32Tile = 128 * 128;                 // one operand tile: 128 rows x 128 bytes = 16 KB
+constexpr int kF32StageBytes = 4 * kF32Tile;        // A_hi, A_lo, B_hi, B_lo
+constexpr int kF32CBytes = (kF32MaxBN / 32) * kF32Tile;     // output staging: 4 boxes of 128 x 32 floats
+constexpr int kF32Threads = 320;
+constexpr int kF32SmemBytes = kF32Stages * kF32StageBytes + kF32CBytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*slack*/;
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 
-int make_map(CUtensorMap *map, const void *base, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-             bool store = false) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) {
-        set_error("cuTensorMapEncodeTiled is unavailable in this driver");
-        return SIRGCN_EUNSUP;
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int bn) {
+    uint32_t d = 0;
+    d |= 1u << 4;                                    // D format: F32
+    d |= 2u << 7;                                    // A format: TF32
+    d |= 2u << 10;                                   // B format: TF32
+    d |= (uint32_t)(bn >> 3) << 17;                  // N >> 3
+    d |= (uint32_t)(kBM >> 4) << 24;                 // M >> 4
+    return d;
+}
+
+// hi = fp32 rounded to the nearest TF32 (low 13 mantissa bits cleared), lo = x - hi (exact)
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = x - hi;
+}
+
+__global__ void __launch_bounds__(kF32Threads, 1)
+gemm_tn_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_c, const float *__restrict__ bias, int M, int N, int K, int bn) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    unsigned char *s_c = smem + kF32Stages * kF32StageBytes;
+    float *s_bias = reinterpret_cast<float *>(s_c + kF32CBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_c + kF32CBytes + 1024);
+    // bars: full[S], split[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base word
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * kF32Stages + 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto split_bar = [&](int s) { return bar0 + 8u * (kF32Stages + s); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * kF32Stages + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (3 * kF32Stages + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (3 * kF32Stages + 2 + s); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + bn - 1) / bn;
+    const int tiles = m_tiles * n_tiles, kblocks = (K + kF32BK - 1) / kF32BK;
+    const int bnp = (bn + 31) & ~31;
+    int tmem_cols = 32;
+    while (tmem_cols < 2 * bnp) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kF32Stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(split_bar(s), 128);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     }
-    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, dtype == SIRGCN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, store ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (CUresult %d) for a %lld x %lld table, ld %lld", (int)r, (long long)rows,
-                  (long long)cols, (long long)ld);
-        return SIRGCN_EINVAL;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    return SIRGCN_OK;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t b_bytes = (uint32_t)bn * 128u;
+
+    if (warp == 0) {
+        // ===== TMA producer: raw fp32 tiles into the A_hi / B_hi slots =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * bn;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), (uint32_t)kF32Tile + b_bytes);
+                    const uint32_t sa = smem_u32(smem + stage * kF32StageBytes);
+                    tma_load_2d(sa, &map_a, full_bar(stage), kb * kF32BK, m0);
+                    tma_load_2d(sa + 2 * kF32Tile, &map_b, full_bar(stage), kb * kF32BK, n0);
+                    if (++stage == kF32Stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: three TF32 products per K step =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(bn);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar(as), aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * bnp);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(split_bar(stage), phase);         // hi / lo tiles are in place and visible to the async proxy
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kF32StageBytes);
+                    const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + kF32Tile);
+                    const uint64_t b_hi = umma_desc(sa + 2 * kF32Tile), b_lo = umma_desc(sa + 3 * kF32Tile);
+#pragma unroll
+                    for (int k = 0; k < kF32BK / 8; ++k) {      // 8 floats = 32 bytes along K inside the swizzle row
+                        const uint64_t o = (uint64_t)(k * 2);
+                        tc_mma_tf32(tmem_d, a_lo + o, b_hi + o, idesc, (kb | k) != 0);
+                        tc_mma_tf32(tmem_d, a_hi + o, b_lo + o, idesc, 1);
+                        tc_mma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, 1);
+                    }
+                    tc_commit(empty_bar(stage));
+                    if (++stage == kF32Stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(as));
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 6) {
+        // ===== splitter: tile -> (hi in place, lo in the twin tile) =====
+        const int tid = threadIdx.x - 192;
+        int stage = 0;
+        uint32_t phase = 0;
+        const int b_vec = (int)(b_bytes >> 4);
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                const uint32_t sa = smem_u32(smem + stage * kF32StageBytes);
+                for (int part = 0; part < 2; ++part) {
+                    const uint32_t base = sa + (uint32_t)part * 2u * kF32Tile;
+                    const int n_vec = part == 0 ? kF32Tile / 16 : b_vec;
+                    for (int i = tid; i < n_vec; i += 128) {
+                        const uint32_t addr = base + (uint32_t)i * 16u;
+                        float4 v, hi, lo;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+                        split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+                        split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kF32Tile), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic writes -> visible to the tensor core
+                mbar_arrive(split_bar(stage));
+                if (++stage == kF32Stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lanes [32q, 32q+32), q = warp % 4 =====
+        const int q = warp & 3;
+        int as = 0;
+        uint32_t aphase = 0;
+        int bias_n0 = -1;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * bn;
+            if (bias != nullptr && n0 != bias_n0) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int j = threadIdx.x - 64; j < bnp; j += 128) s_bias[j] = (j < bn && n0 + j < N) ? bias[n0 + j] : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                bias_n0 = n0;
+            }
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int r = q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bnp);
+            const uint32_t srow = smem_u32(s_c) + (uint32_t)r * 128u;
+            for (int c0 = 0; c0 < bnp; c0 += 32) {              // one 128 x 32 box per 32 accumulator columns
+                uint32_t v[32];
+                tc_ld32(taddr + (uint32_t)c0, v);
+                tc_wait_ld();
+                const uint32_t box = srow + (uint32_t)(c0 >> 5) * kF32Tile;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float f[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) f[i] = __uint_as_float(v[4 * j + i]) + (bias ? s_bias[c0 + 4 * j + i] : 0.f);
+                    const uint32_t dst = box + ((uint32_t)(j ^ (r & 7)) << 4);        // SWIZZLE_128B
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+                for (int b = 0; b * 32 < bn; ++b)
+                    tma_store_2d(&map_c, smem_u32(s_c) + (uint32_t)b * kF32Tile, n0 + b * 32, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
 }
 
 }  // namespace
@@ -317,10 +439,33 @@ int make_map(CUtensorMap *map, const void *base, int dtype, int64_t rows, int64_
 extern "C" int sirgcn_gemm_tn(const void *a, int64_t lda, const void *b, int64_t ldb, void *c, int64_t ldc,
                               const float *bias, int64_t m, int32_t n, int32_t k, int32_t dtype, void *stream) {
     using namespace sirgcn;
-    SIRGCN_CHECK_ARG(dtype == SIRGCN_BF16 || dtype == SIRGCN_F16, "sirgcn_gemm_tn handles bf16/fp16 tables (dtype %d)", dtype);
+    SIRGCN_CHECK_ARG(dtype == SIRGCN_BF16 || dtype == SIRGCN_F16 || dtype == SIRGCN_F32, "bad dtype %d", dtype);
     SIRGCN_CHECK_ARG(m >= 0 && m < (1LL << 31) && n > 0 && k > 0, "bad shape m=%lld n=%d k=%d", (long long)m, n, k);
     if (m == 0) return SIRGCN_OK;
     SIRGCN_CHECK_ARG(a && b && c, "a/b/c is NULL");
+    if (dtype == SIRGCN_F32) {
+        SIRGCN_CHECK_ARG(n % 4 == 0 && k % 4 == 0, "n and k must be multiples of 4 (16-byte rows): n=%d k=%d", n, k);
+        SIRGCN_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(c) && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 &&
+                             lda >= k && ldb >= k && ldc >= n, "operands must have 16-byte aligned rows");
+        const int bn = n >= kF32MaxBN ? kF32MaxBN : (n + 15) / 16 * 16;
+        CUtensorMap map_a, map_b, map_c;
+        int rc = make_map(&map_a, a, dtype, m, k, lda, kBM);
+        if (rc) return rc;
+        rc = make_map(&map_b, b, dtype, n, k, ldb, bn);
+        if (rc) return rc;
+        rc = make_map(&map_c, c, dtype, m, n, ldc, kBM, true);
+        if (rc) return rc;
+        const int tiles = (int)((m + kBM - 1) / kBM) * ((n + bn - 1) / bn);
+        static std::atomic<bool> configured32{false};
+        if (!configured32.load(std::memory_order_relaxed)) {
+            SIRGCN_CUDA(cudaFuncSetAttribute(gemm_tn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF32SmemBytes));
+            configured32.store(true, std::memory_order_relaxed);
+        }
+        gemm_tn_f32_kernel<<<std::min(tiles, kNumSMs), kF32Threads, kF32SmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+            map_a, map_b, map_c, bias, (int)m, n, k, bn);
+        SIRGCN_LAUNCHED();
+        return SIRGCN_OK;
+    }
     SIRGCN_CHECK_ARG(n % 8 == 0 && k % 8 == 0, "n and k must be multiples of 8 (16-byte rows): n=%d k=%d", n, k);
     SIRGCN_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(c) && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 &&
                          lda >= k && ldb >= k && ldc >= n, "operands must have 16-byte aligned rows");

@@ -310,8 +310,11 @@ class SIRLayerFunction(torch.autograd.Function):
         need = ctx.needs_input_grad
         gout = gout.to(qk.dtype)
         gout = gout if gout.stride(-1) == 1 else gout.contiguous()
-        dw_r = gemm.linear_wgrad(gout, a, w_r.dtype) if need[4] else None
-        db_r = gemm.column_sum(gout, w_r.dtype) if (need[5] and ctx.has_bias[1]) else None
+        dw_r = db_r = None
+        if need[4]:         # the bias gradient rides along in the same pass over gout
+            dw_r, db_r = gemm.linear_wgrad_bias(gout, a, w_r.dtype, need[5] and ctx.has_bias[1])
+        elif need[5] and ctx.has_bias[1]:
+            db_r = gemm.column_sum(gout, w_r.dtype)
         da = gemm.linear_dgrad(gout, w_r.to(qk.dtype), pad_to=_pad_cols(d, qk.dtype))[:, :d]   # [N, d]
         da._sirgcn_padded = True
         ds, ss = g.scales(ctx.agg_type)
@@ -345,8 +348,11 @@ class SIRLayerFunction(torch.autograd.Function):
             hq._sirgcn_padded = hk._sirgcn_padded = True
             mask_scale_(hk, keep_k, ctx.drop_scale)
             mask_scale_(hq, keep_q, ctx.drop_scale)
-        dw_qk = gemm.linear_wgrad(dqk, feat, w_qk.dtype) if need[1] else None
-        db_qk = gemm.column_sum(dqk, w_qk.dtype) if (need[2] and ctx.has_bias[0]) else None
+        dw_qk = db_qk = None
+        if need[1]:
+            dw_qk, db_qk = gemm.linear_wgrad_bias(dqk, feat, w_qk.dtype, need[2] and ctx.has_bias[0])
+        elif need[2] and ctx.has_bias[0]:
+            db_qk = gemm.column_sum(dqk, w_qk.dtype)
         dfeat = gemm.linear_dgrad(dqk, w_qk.to(dqk.dtype)).to(feat.dtype) if need[0] else None
         if de is not None and ix_csr is not None:
             de = de.to(w_qk.dtype)                  # the table's gradient, in the parameter's dtype

@@ -5,9 +5,9 @@ All three GEMM shapes are "TN" products of row-major operands:
     forward   C[M, N]  = X[M, K] · W[N, K]^T (+ b)
     dgrad     dX[M, K] = dY[M, N] · W[N, K]          = dY · (W^T)^T
     wgrad     dW[N, K] = dY[M, N]^T · X[M, K]
-bf16 operands on CUDA go to the hand-written tcgen05/TMEM/TMA kernel when it is built in;
-fp32 operands keep ATen's SGEMM (TF32 off, as in the reference) because tcgen05 has no
-IEEE-fp32 MMA and the fp32 parity target is 1e-5 relative.
+16-bit operands on CUDA go to the hand-written tcgen05/TMEM/TMA kernel; fp32 operands go to its 3xTF32 variant
+(hi/lo split in shared memory, three kind::tf32 MMAs per K step, fp32 accumulation in TMEM: ~1e-6 relative, inside
+the 1e-5 fp32 parity target that a single TF32 product misses — tcgen05 has no IEEE-fp32 MMA).
 """
 from __future__ import annotations
 
@@ -19,14 +19,16 @@ import torch.nn.functional as F
 
 from . import _lib
 
-# SIRGCN_GEMM=cublas routes the 16-bit projections through the library instead (A/B measurements)
+# SIRGCN_GEMM=cublas routes the projections through the library instead (A/B measurements); SIRGCN_GEMM32=cublas
+# only the fp32 ones
 _USE_TC = os.environ.get("SIRGCN_GEMM", "tcgen05") != "cublas"
+_USE_TC32 = _USE_TC and os.environ.get("SIRGCN_GEMM32", "tcgen05") != "cublas"
 
 
 def _rows16(t):
-    """2-D, unit column stride, 16-byte aligned rows of a 16-bit table"""
+    """2-D, unit column stride, 16-byte aligned rows"""
     return (t.dim() == 2 and t.stride(1) == 1 and t.data_ptr() % 16 == 0 and
-            (t.shape[0] <= 1 or t.stride(0) % 8 == 0))
+            (t.shape[0] <= 1 or (t.stride(0) * t.element_size()) % 16 == 0))
 
 
 def _ld(t):
@@ -34,9 +36,15 @@ def _ld(t):
 
 
 def tc_eligible(x, n, k):
-    """the hand-written tcgen05 kernel handles CUDA bf16/fp16 operands with 16-byte rows (n, k multiples of 8)"""
-    return (_USE_TC and x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and n % 8 == 0 and k % 8 == 0
-            and x.shape[0] < 2 ** 31)
+    """the hand-written tcgen05 kernels handle CUDA bf16 / fp16 / fp32 operands whose rows are whole 16-byte vectors
+    (n, k multiples of 8 for 16-bit, of 4 for fp32)"""
+    if not x.is_cuda or x.shape[0] >= 2 ** 31:
+        return False
+    if x.dtype in (torch.bfloat16, torch.float16):
+        return _USE_TC and n % 8 == 0 and k % 8 == 0
+    if x.dtype == torch.float32:
+        return _USE_TC32 and n % 4 == 0 and k % 4 == 0
+    return False
 
 
 def gemm_tn(a, b, bias=None, out=None):
@@ -118,6 +126,34 @@ def linear_dgrad(dy, weight, pad_to=None, out=None):
     return out
 
 
+def wgrad_tc_eligible(dy, x):
+    return (_USE_TC and os.environ.get("SIRGCN_WGRAD", "tcgen05") != "cublas" and dy.is_cuda and x.is_cuda
+            and dy.dtype in (torch.bfloat16, torch.float16) and x.dtype == dy.dtype and dy.dim() == 2 and x.dim() == 2
+            and dy.shape[1] % 8 == 0 and x.shape[1] % 8 == 0 and dy.shape[0] < 2 ** 31 and _rows16(dy) and _rows16(x))
+
+
+def linear_wgrad_bias(dy, x, out_dtype, want_bias):
+    """(dW = dY^T · X, db = column sums of dY or None): for 16-bit tables ONE pass of the hand-written tcgen05 kernel
+    over both tables (sirgcn_gemm_wgrad: MN-major operands, node dimension split over the SMs, bias as an extra MMA
+    against a tile of ones); otherwise the library GEMM + sirgcn_colsum.  fp32 accumulation either way."""
+    if wgrad_tc_eligible(dy, x):
+        m, n_out, k_in = dy.shape[0], dy.shape[1], x.shape[1]
+        L = _lib.lib()
+        dw = torch.empty((n_out, k_in), dtype=torch.float32, device=dy.device)
+        db = torch.empty(n_out, dtype=torch.float32, device=dy.device) if want_bias else None
+        nbytes = L.sirgcn_gemm_wgrad_workspace_bytes(C.c_int64(m), C.c_int32(n_out), C.c_int32(k_in))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device)
+        with torch.cuda.device(dy.device):
+            rc = L.sirgcn_gemm_wgrad(_lib.ptr(dy), C.c_int64(_ld(dy)), _lib.ptr(x), C.c_int64(_ld(x)), C.c_int64(m),
+                                     C.c_int32(n_out), C.c_int32(k_in), C.c_int32(_lib.DTYPE_CODE[dy.dtype]),
+                                     _lib.ptr(dw), C.c_int64(k_in), _lib.ptr(db), _lib.ptr(ws), C.c_size_t(nbytes),
+                                     _lib.stream_ptr(dy.device))
+        _lib.check(rc, "sirgcn_gemm_wgrad")
+        return dw.to(out_dtype), (None if db is None else db.to(out_dtype))
+    dw = (dy.t() @ x.to(dy.dtype)).to(out_dtype)
+    return dw, (column_sum(dy, out_dtype) if want_bias else None)
+
+
 def linear_wgrad(dy, x, out_dtype):
     """dW = dY^T · X, accumulated in fp32 by the GEMM, returned in the parameter dtype"""
-    return (dy.t() @ x.to(dy.dtype)).to(out_dtype)
+    return linear_wgrad_bias(dy, x, out_dtype, False)[0]

@@ -687,9 +687,11 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                 da_sl, da_full, da_handles = prepared                     # sent chunk by chunk under the dK walk above
                 prepared = None
                 da = _table(da_sl.local, n, d)
-            if wneed[l][3]:
-                grads[l][3] = (g.t() @ a).to(adt)
-            if wneed[l][4] and b_r is not None:
+            if wneed[l][3]:     # dW_R and db_R in one pass over g (tcgen05 wgrad kernel for 16-bit tables)
+                grads[l][3], db_ = gemm.linear_wgrad_bias(g, a, adt, bool(wneed[l][4] and b_r is not None))
+                if db_ is not None:
+                    grads[l][4] = db_
+            elif wneed[l][4] and b_r is not None:
                 grads[l][4] = gemm.column_sum(g, adt)
             q, k = _table(q_sl.local, n, d), _table(k_sl.local, n, d)
             kf, daf = _table(k_all, k_all.shape[0], d), _table(da_full, da_full.shape[0], d)
@@ -768,10 +770,13 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
             for key in ("q_full", "q_h", "k_all", "a", "k_sl", "q_sl", "h_full", "q_all_kept"):
                 st[key] = None
             featd = feat.to(dt)
+            want_bq = bool(wneed[l][1] and b_q is not None)
             if wneed[l][0] or wneed[l][2]:
-                dw_qk = (dqk.t() @ featd).to(adt)                          # [2·ld, d_in]
+                dw_qk, db_qk = gemm.linear_wgrad_bias(dqk, featd, adt, want_bq)     # [2·ld, d_in], [2·ld]
                 grads[l][0], grads[l][2] = dw_qk[:d], dw_qk[ld:ld + d]
-            if wneed[l][1] and b_q is not None:
+                if db_qk is not None:
+                    grads[l][1] = db_qk[:d]
+            elif want_bq:
                 grads[l][1] = gemm.column_sum(dqk, adt)[:d]
             st["h"] = None
             del feat, featd, dqk
