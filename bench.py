@@ -350,7 +350,8 @@ def partition_parity_check(args, w, layers, dev, rank, world):
         torch.set_num_threads(os.cpu_count() or 1)
         ref = small_layers(w, RefSIRConv, None).double()
         # what the reference run in the table dtype sees: weights and stored tables rounded to it (oracle header)
-        ref.load_state_dict({k: v.detach().to(dtype).cpu().double() for k, v in layers.state_dict().items()})
+        ref.load_state_dict({k: (v.detach().to(dtype) if v.dim() > 1 else v.detach()).cpu().double()
+                             for k, v in layers.state_dict().items()})     # matrices are cast per call, biases stay fp32
         for l in ref:
             l.storage_dtype = None if dtype == torch.float32 else dtype
         xr = x.detach().cpu().double().requires_grad_(True)

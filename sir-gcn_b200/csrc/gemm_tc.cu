@@ -208,15 +208,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 // =====================================================================================================================
 // fp32 tables: C[M, N] = A[M, K] · B[N, K]^T (+ bias) in fp32 on the tensor cores by the 3xTF32 split
-//     a = a_hi + a_lo,  a_hi = a rounded to TF32 (10 explicit mantissa bits), a_lo = a - a_hi (exact in fp32)
-//     a·b ≈ a_hi·b_hi + a_lo·b_hi + a_hi·b_lo            (the dropped a_lo·b_lo is 2^-22 relative)
-// fp32 accumulation in TMEM; measured ~1e-6 relative against fp64, inside the 1e-5 fp32 parity target that plain TF32
+//     a ≈ a_hi + a_lo,  a_hi = a rounded to TF32 (10 explicit mantissa bits), a_lo = (a - a_hi) rounded to TF32
+//     a·b ≈ a_hi·b_hi + a_lo·b_hi + a_hi·b_lo + a_lo·b_lo          (representation error 2^-23 per operand)
+// fp32 accumulation in TMEM; measured ~1e-7 relative against fp64, inside the 1e-5 fp32 parity target that plain TF32
 // (1e-3) misses and that made round 1 keep the library SGEMM (tcgen05 has no IEEE fp32 MMA).  The reference computes
 // these projections with cuBLAS SGEMM (/root/reference/models/conv.py:60-61,:65).
 // Same structure as gemm_tn_kernel plus a SPLITTER warpgroup: TMA lands the raw fp32 tiles (128-byte swizzled rows of
 // 32 floats); warps 6-9 rewrite each tile in place as its hi part and write the lo part to a twin tile at the same
 // offsets (an elementwise rewrite keeps the swizzle), fence to the async proxy and hand the stage to the MMA warp,
-// which issues three kind::tf32 MMAs per 8-wide K step.
+// which issues four kind::tf32 MMAs per 8-wide K step.
 // =====================================================================================================================
 constexpr int kF32BK = 32;                          // fp32 elements per 128-byte swizzle row
 constexpr int kF32MaxBN = 128;
@@ -245,10 +245,13 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int bn) {
     return d;
 }
 
-// hi = fp32 rounded to the nearest TF32 (low 13 mantissa bits cleared), lo = x - hi (exact)
+// hi = x rounded to the nearest TF32 (10 explicit mantissa bits), lo = (x - hi) rounded to the nearest TF32 as well:
+// the tensor core TRUNCATES the low 13 mantissa bits of what it reads, so a residual left at 13 significant bits would
+// lose up to 2^-21·|x|; rounded here, x = hi + lo to within 2^-23·|x|
+__device__ __forceinline__ float rn_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-    lo = x - hi;
+    hi = rn_tf32(x);
+    lo = rn_tf32(x - hi);
 }
 
 __global__ void __launch_bounds__(kF32Threads, 1)
@@ -272,8 +275,13 @@ gemm_tn_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + bn - 1) / bn;
     const int tiles = m_tiles * n_tiles, kblocks = (K + kF32BK - 1) / kF32BK;
     const int bnp = (bn + 31) & ~31;
+    // two accumulators per stage: the hi·hi products, and the three small correction products.  The tensor core adds
+    // into its fp32 accumulator with TRUNCATION (measured: a one-sided error growing linearly with the number of
+    // accumulation steps, 9e-7 at K = 128 with all four products in one accumulator); the corrections are 2^-11 of
+    // the result, so their accumulator's truncation is negligible, and the main one sees a quarter of the steps.  The
+    // epilogue adds the two in fp32 (round to nearest).
     int tmem_cols = 32;
-    while (tmem_cols < 2 * bnp) tmem_cols <<= 1;
+    while (tmem_cols < 4 * bnp) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kF32Stages; ++s) {
@@ -326,7 +334,7 @@ gemm_tn_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
                 mbar_wait(tempty_bar(as), aphase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(as * bnp);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * 2 * bnp), tmem_c = tmem_d + (uint32_t)bnp;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(split_bar(stage), phase);         // hi / lo tiles are in place and visible to the async proxy
                     tc_fence_after();
@@ -336,9 +344,10 @@ gemm_tn_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
                     for (int k = 0; k < kF32BK / 8; ++k) {      // 8 floats = 32 bytes along K inside the swizzle row
                         const uint64_t o = (uint64_t)(k * 2);
-                        tc_mma_tf32(tmem_d, a_lo + o, b_hi + o, idesc, (kb | k) != 0);
-                        tc_mma_tf32(tmem_d, a_hi + o, b_lo + o, idesc, 1);
-                        tc_mma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, 1);
+                        tc_mma_tf32(tmem_c, a_lo + o, b_lo + o, idesc, (kb | k) != 0);     // 2^-22: smallest first
+                        tc_mma_tf32(tmem_c, a_lo + o, b_hi + o, idesc, 1);
+                        tc_mma_tf32(tmem_c, a_hi + o, b_lo + o, idesc, 1);
+                        tc_mma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, (kb | k) != 0);
                     }
                     tc_commit(empty_bar(stage));
                     if (++stage == kF32Stages) { stage = 0; phase ^= 1; }
@@ -394,12 +403,15 @@ gemm_tn_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const int r = q * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bnp);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * bnp);
             const uint32_t srow = smem_u32(s_c) + (uint32_t)r * 128u;
             for (int c0 = 0; c0 < bnp; c0 += 32) {              // one 128 x 32 box per 32 accumulator columns
-                uint32_t v[32];
+                uint32_t v[32], vc[32];
                 tc_ld32(taddr + (uint32_t)c0, v);
+                tc_ld32(taddr + (uint32_t)(bnp + c0), vc);
                 tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vc[i]));
                 const uint32_t box = srow + (uint32_t)(c0 >> 5) * kF32Tile;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {

@@ -105,6 +105,9 @@ EncodeTiledFn encode_fn() {
 
 int make_map(CUtensorMap *map, const void *base, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows,
              bool store = false) {
+    // The encode call is a DRIVER entry point and wants a current context; an autograd worker thread whose first CUDA
+    // call is this one has none yet (the runtime binds the primary context lazily): bind it.
+    cudaFree(nullptr);
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is unavailable in this driver");

@@ -288,6 +288,7 @@ class SIRLayerFunction(torch.autograd.Function):
         ctx.save_for_backward(feat, qk, e, a, w_qk, w_r, b_qk if recompute_qk else None, keep_q, keep_k)
         ctx.graph, ctx.agg_type, ctx.act, ctx.act_param, ctx.d = graph, agg_type, act, act_param, d
         ctx.drop_scale = drop_scale
+        ctx.e_index = (ix_csr, ix_csc)
         ctx.has_bias = (b_qk is not None, b_r is not None)
         ctx.lean = bool(recompute_qk)      # the re-made [Q|K] belongs to backward alone: it may be overwritten
         return out
