@@ -536,7 +536,10 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                     w_cat_f[ld:ld + d].copy_(w_k)
                     b_cat_f = None
                     if b_q is not None:
-                        b_cat_f = torch.zeros(2 * ld, dtype=dt, device=dev)
+                        # in the parameter's own dtype: the projection adds the bias in fp32, exactly as the local Q
+                        # projection below does — a bias rounded to the table dtype here would give the backward CSC
+                        # walk (which reads THIS table) other pre-activation signs than the forward walk saw
+                        b_cat_f = torch.zeros(2 * ld, dtype=b_q.dtype, device=dev)
                         b_cat_f[:d].copy_(b_q)
                     qk_all = gemm.linear_forward(h_full.to(dt), w_cat_f, b_cat_f)       # [rows_all, 2·ld]
                     k_all = qk_all[:, ld:2 * ld]            # row stride 2·ld: the walks take any 16-byte row pitch

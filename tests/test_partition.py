@@ -184,7 +184,8 @@ def _run_gloo(world, agg, act, n_layers, chunks, use_full, gather, bwd_chunks, l
 
 
 @pytest.mark.parametrize("world,agg,act,n_layers,chunks,use_full,gather,bwd_chunks,layout,keep_q", [
-    (2, "mean", "relu", 2, 4, True, "projections", 4, 4, None),     # the bench's schedule: cuts == layout chunks
+    (2, "mean", "relu", 2, 4, True, "projections", 4, 4, None),     # cuts == layout chunks, dA under the dK walk
+    (2, "mean", "relu", 2, 4, True, "projections", 1, 4, None),     # the bench's default schedule
     (2, "sym", "leaky", 2, 2, True, "projections", 1, 4, False),    # cuts of two layout chunks each
     (2, "sym", "gelu", 3, 4, False, "projections", 2, 4, None),     # no gathered input: K and Q travel
     (2, "mean", "leaky", 2, 3, True, "inputs", 3, 4, None),         # cuts that split layout chunks (partial pieces)
