@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIRGCN_ABI_VERSION 8
+#define SIRGCN_ABI_VERSION 9
 
 /* element types of feature tables (accumulation is always fp32) */
 enum { SIRGCN_F32 = 0, SIRGCN_BF16 = 1, SIRGCN_F16 = 2 };
@@ -194,7 +194,13 @@ typedef struct sirgcn_edge_args {
      * (sirgcn_etable_grad) => bitwise repeatable, no atomics.  n_etypes <= SIRGCN_MAX_ETYPES. */
     int32_t n_etypes;
     float *de_partial;
+    /* SIRGCN_WALK_PLAIN_GRID: one CTA per 4 work units instead of persistent warps on a grid of the resident CTAs.
+     * Persistent walks are ~6 % faster alone, but their CTAs hold every SM until the walk ends; a plain grid retires a
+     * CTA every few tens of microseconds, which is what lets a collective's kernels (NCCL all-gathers of the row
+     * partition) become resident WHILE a walk runs. */
+    int32_t flags;
 } sirgcn_edge_args;
+#define SIRGCN_WALK_PLAIN_GRID 1
 #define SIRGCN_MAX_ETYPES 8
 
 /* dTable[t, c] = sum over work units u (in index order) of de_partial[u, t, c]; out is fp32 [n_etypes, ld_out]. */

@@ -10,7 +10,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIRGCN_LIB") or os.path.join(_HERE, "libsirgcn.so")   # override: kernel-variant A/B runs
 
-ABI_VERSION = 8     # include/sirgcn.h SIRGCN_ABI_VERSION
+ABI_VERSION = 9     # include/sirgcn.h SIRGCN_ABI_VERSION
+WALK_PLAIN_GRID = 1  # sirgcn_edge_args.flags
 MAX_ETYPES = 8      # SIRGCN_MAX_ETYPES
 F32, BF16, F16 = 0, 1, 2
 ACT_IDENTITY, ACT_RELU, ACT_LEAKY_RELU, ACT_GELU = 0, 1, 2, 3
@@ -50,7 +51,7 @@ class EdgeArgs(C.Structure):
         ("sched", Schedule), ("n_long", C.c_int32), ("n_chunks", C.c_int32),
         ("partial", C.c_void_p),
         ("tile_row", C.c_void_p), ("n_tiles", C.c_int32), ("accumulate", C.c_int32),
-        ("n_etypes", C.c_int32), ("de_partial", C.c_void_p),
+        ("n_etypes", C.c_int32), ("de_partial", C.c_void_p), ("flags", C.c_int32),
     ]
 
 

@@ -802,7 +802,7 @@ int launch_gs(const sirgcn_edge_args &a, cudaStream_t st) {
     if (!ctr_base) SIRGCN_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&ctr_base), g_unit_ctr));
     auto walk = [&](int n_units, int chunk_mode) -> int {
         const int grid_all = (n_units + kWarps - 1) / kWarps;
-        if (no_persist || grid_all <= cap) {                     // everything is resident at once anyway
+        if (no_persist || (a.flags & SIRGCN_WALK_PLAIN_GRID) || grid_all <= cap) {   // (or: everything is resident at once anyway)
             kern<<<(unsigned)grid_all, kWarps * 32, smem, st>>>(a, chunk_mode, nullptr);
         } else {
             unsigned int *ctr = ctr_base + (g_ctr_next.fetch_add(1, std::memory_order_relaxed) % kCtrSlots);

@@ -99,6 +99,11 @@ def _ld(t):
     return t.stride(0) if t.shape[0] > 1 else _pad_cols(t.shape[1], t.dtype)
 
 
+# Persistent walks (a grid of the resident CTAs + a device work-unit counter) are the default; the row-partitioned stack
+# (partition.py) switches to plain grids while it runs at more than one rank, so that the collectives' kernels can become
+# resident under a walk (include/sirgcn.h SIRGCN_WALK_PLAIN_GRID).
+WALK_PERSISTENT = True
+
 # bench.py sets this to a list to collect (entry point, start event, end event, (positions, rows)) of every edge
 # call, recorded on the stream the kernels are launched on (roofline measurement); None = off
 EDGE_TIMERS = None
@@ -136,6 +141,7 @@ def _edge_call(fn_name, rows: CompressedRows, d, dtype, act, act_param, q, k, da
     a.tile_row = None if rows.tile_row is None else rows.tile_row.data_ptr()
     a.n_tiles = rows.n_tiles
     a.accumulate = 1 if accumulate else 0
+    a.flags = 0 if WALK_PERSISTENT else _lib.WALK_PLAIN_GRID
     if de_partial is not None:
         a.n_etypes, a.de_partial = e.shape[0], de_partial.data_ptr()
     dev = rows.indptr.device

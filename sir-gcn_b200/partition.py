@@ -483,6 +483,25 @@ def _table(buf, n, d):
     return t
 
 
+class _walk_mode:
+    """plain-grid edge walks while a stack runs on more than one rank (the collectives' kernels must be able to become
+    resident under a walk; persistent walk CTAs would hold every SM until the walk ends — function.WALK_PERSISTENT).
+    SIRGCN_PARTITION_PERSIST=1 keeps the persistent walks (for measurements)."""
+
+    def __init__(self, part):
+        import os
+        self.plain = part.world > 1 and os.environ.get("SIRGCN_PARTITION_PERSIST", "0") != "1"
+
+    def __enter__(self):
+        self.saved = F_.WALK_PERSISTENT
+        if self.plain:
+            F_.WALK_PERSISTENT = False
+
+    def __exit__(self, *exc):
+        F_.WALK_PERSISTENT = self.saved
+        return False
+
+
 class PartitionedSIRStackFunction(torch.autograd.Function):
     """L stacked SIRConv layers (sum / mean / sym, elementwise σ, no dropout, nothing between the layers) on a
     row-partitioned graph as ONE autograd node — the unit that can hide the table traffic (module docstring):
@@ -500,6 +519,11 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat, part: RowPartition, cfgs, opts, backend, feat_full, *weights):
+        with _walk_mode(part):
+            return PartitionedSIRStackFunction._forward(ctx, feat, part, cfgs, opts, backend, feat_full, *weights)
+
+    @staticmethod
+    def _forward(ctx, feat, part: RowPartition, cfgs, opts, backend, feat_full, *weights):
         L = len(cfgs)
         W = [weights[5 * l:5 * l + 5] for l in range(L)]
         n, dt, dev = part.n_local, feat.dtype, feat.device
@@ -526,9 +550,9 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
                 rows_all = h_full.shape[0]
                 keep = opts.get("keep_q_full")
                 if keep is None:    # auto: ONE [Q|K] GEMM over the gathered input, Q kept for the backward CSC walk,
-                    # when the extra table fits comfortably (8 GPUs: yes; 2 GPUs on the 2 B-edge graph: no)
-                    keep = train and (not h_full.is_cuda or
-                                      torch.cuda.mem_get_info(dev)[0] > 4 * rows_all * ld * h_full.element_size())
+                    # when the extra table fits comfortably (from 4 GPUs up; at 2 GPUs the 2 B-edge graph leaves no room for it)
+                    keep = train and (not h_full.is_cuda or (part.world >= 4 and
+                                      torch.cuda.mem_get_info(dev)[0] > 4 * rows_all * ld * h_full.element_size()))
                 q_all_kept = None
                 if keep and train:
                     w_cat_f = (torch.zeros if ld != d else torch.empty)((2 * ld, w_q.shape[1]), dtype=dt, device=dev)
@@ -650,6 +674,11 @@ class PartitionedSIRStackFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
+        with _walk_mode(ctx.part):
+            return PartitionedSIRStackFunction._backward(ctx, gout)
+
+    @staticmethod
+    def _backward(ctx, gout):
         L, part, be, leases, state = ctx.L, ctx.part, ctx.backend, ctx.leases, ctx.state
         tensors = ctx.saved_tensors
         feat0, feat_full, weights = tensors[0], tensors[1], tensors[2:]

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     for name in declared_functions():
         assert hasattr(lib, name), f"{name} declared in sirgcn.h but not exported"
     lib.sirgcn_abi_version.restype = ctypes.c_int
-    assert lib.sirgcn_abi_version() == 8
+    assert lib.sirgcn_abi_version() == 9
     lib.sirgcn_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.sirgcn_last_error(), bytes)
 
