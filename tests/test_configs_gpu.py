@@ -116,8 +116,9 @@ def test_cifar_superpixel_shaped_batch_four_layers(agg):
         # resolves, and whether σ' flips for them differs between ANY two fp32 evaluations (the oracle's own fp32 run
         # included) — one flip moves a whole row of the upstream gradient by O(1e-4) of the tensor max.  Outputs are held
         # to the max-abs tolerance; gradients are compared in the Frobenius norm, which a few flipped elements out of
-        # millions do not move.
-        check_stack(ref, gpu, src, dst, n, x, efeat, grad_metric=fro_err, grad_tol=1e-4)
+        # millions do not move.  (Measured on the CPU oracle alone: its fp32 run differs from its fp64 run by 1e-4 ..
+        # 3e-4 on these gradients in either metric, and which parameters are hit changes with the machine's BLAS.)
+        check_stack(ref, gpu, src, dst, n, x, efeat, grad_metric=fro_err, grad_tol=1e-3)
     else:
         # 7.7 M maxima over 8 candidates: a handful have their two best candidates closer than fp32 resolves, and
         # fp32 then routes that element's gradient to the other edge than the fp64 oracle.  The forward value is
