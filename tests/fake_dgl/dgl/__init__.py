@@ -5,7 +5,10 @@ Purpose: let the UNMODIFIED reference layer (`models/conv.py`, which does `from 
 tests/golden/ are produced by the reference's own code and (b) the restated oracle (oracle/sirconv_ref.py) is
 checked against it.  DGL itself (dgl==2.1.0, requirements.txt:1) is not installable here.
 
-Only the documented semantics of the eight symbols the layer uses are modelled:
+The documented semantics of the eight symbols the layer uses are modelled (first block); a few more (second block)
+exist so that the reference's own MODEL files (synthetic-datasets/*/model.py, which import models.utils and with it
+dgl.transforms.DropEdge, and use dgl.nn.SumPooling) import and run unmodified for the CPU plumbing of BASELINE.json
+configs[0]:
 
     dgl.graph((src, dst), num_nodes=)      homogeneous multigraph, edge id = position in the COO list
     g.num_nodes() / g.num_edges() / g.device / g.edges(form, order) / g.in_degrees() / g.out_degrees()
@@ -18,6 +21,12 @@ Only the documented semantics of the eight symbols the layer uses are modelled:
     dgl.function.{sum,mean,max,min}(msg, out)
     dgl.utils.expand_as_pair(feat, g)      (feat, feat) on a homogeneous graph, tuples pass through
 
+    dgl.batch(graphs)                      block-diagonal union: node ids offset, frames concatenated, batch_size /
+                                           batch_num_nodes() kept
+    dgl.rand_graph(n, e)                   random multigraph (self loops allowed), as the hetero-edge-count data uses
+    dgl.transforms.DropEdge(p)(g)          every edge removed independently with probability p; edata follows
+    dgl.nn.SumPooling()(g, feat)           per-graph sums of a batched graph
+
 The reducers are written differently from the oracle on purpose (dense incidence products and per-node Python loops
 instead of index_add_ / scatter_reduce_), so that the two do not share an implementation.
 """
@@ -27,7 +36,7 @@ import contextlib
 
 import torch
 
-from . import function, utils  # noqa: F401
+from . import function, nn, transforms, utils  # noqa: F401
 
 __version__ = "2.1.0+fake"
 
@@ -69,14 +78,23 @@ class DGLGraph:
             raise ValueError("node ids out of range")
         self.ndata = _Frame(self._n)
         self.edata = _Frame(int(self._src.numel()))
+        self._batch_num_nodes = None            # set by dgl.batch
 
     # --- structure queries ---------------------------------------------------------------------------------
     @property
     def device(self):
         return self._src.device
 
+    @property
+    def batch_size(self):
+        return 1 if self._batch_num_nodes is None else int(self._batch_num_nodes.numel())
+
+    def batch_num_nodes(self):
+        return torch.tensor([self._n]) if self._batch_num_nodes is None else self._batch_num_nodes
+
     def to(self, device):
         g = DGLGraph(self._src.to(device), self._dst.to(device), self._n)
+        g._batch_num_nodes = None if self._batch_num_nodes is None else self._batch_num_nodes.to(device)
         for k, v in self.ndata.items():
             g.ndata[k] = v.to(device)
         for k, v in self.edata.items():
@@ -123,6 +141,28 @@ class DGLGraph:
         if m.shape[0] != self.num_edges():
             raise ValueError("message must have one row per edge")
         self.ndata[reduce_func.out_field] = reduce_func.reduce(m, self._dst, self._n)
+
+
+def batch(graphs):
+    """block-diagonal union of homogeneous graphs (node ids offset by the sizes of the graphs before)"""
+    graphs = list(graphs)
+    sizes = torch.tensor([g.num_nodes() for g in graphs])
+    offs = torch.cumsum(sizes, 0) - sizes
+    src = torch.cat([g._src + int(o) for g, o in zip(graphs, offs)]) if graphs else torch.empty(0, dtype=torch.int64)
+    dst = torch.cat([g._dst + int(o) for g, o in zip(graphs, offs)]) if graphs else torch.empty(0, dtype=torch.int64)
+    out = DGLGraph(src, dst, int(sizes.sum()))
+    for key in (graphs[0].ndata.keys() if graphs else ()):
+        out.ndata[key] = torch.cat([g.ndata[key] for g in graphs])
+    for key in (graphs[0].edata.keys() if graphs else ()):
+        out.edata[key] = torch.cat([g.edata[key] for g in graphs])
+    out._batch_num_nodes = sizes
+    return out
+
+
+def rand_graph(num_nodes, num_edges, generator=None):
+    src = torch.randint(0, num_nodes, (num_edges,), generator=generator)
+    dst = torch.randint(0, num_nodes, (num_edges,), generator=generator)
+    return DGLGraph(src, dst, num_nodes)
 
 
 def graph(data, num_nodes=None, idtype=None, device=None):
