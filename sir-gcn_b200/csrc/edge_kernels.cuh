@@ -798,8 +798,12 @@ int launch_gs(const sirgcn_edge_args &a, cudaStream_t st) {
     const int cap = resident.load(std::memory_order_relaxed);
     // unit counters: a ring of words in static device memory (the library allocates nothing); a launch zeroes its
     // word on its own stream just before it runs, and a word comes round again only after kCtrSlots later launches
-    static unsigned int *ctr_base = nullptr;
-    if (!ctr_base) SIRGCN_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&ctr_base), g_unit_ctr));
+    static unsigned int *ctr_bases[64] = {};                     // per device: a __device__ symbol has one address per GPU
+    int dev = 0;
+    SIRGCN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!ctr_bases[dev]) SIRGCN_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&ctr_bases[dev]), g_unit_ctr));
+    unsigned int *const ctr_base = ctr_bases[dev];
     auto walk = [&](int n_units, int chunk_mode) -> int {
         const int grid_all = (n_units + kWarps - 1) / kWarps;
         if (no_persist || (a.flags & SIRGCN_WALK_PLAIN_GRID) || grid_all <= cap) {   // (or: everything is resident at once anyway)
