@@ -23,6 +23,7 @@ constexpr int kWgBox = kWgNodes * 128;          // one box: 64 nodes x 128 bytes
 constexpr int kWgThreads = 192;
 constexpr int kWgMaxMt = 4;                     // MMA-M tiles (128 rows of dW each) per CTA
 constexpr int kWgSmemBudget = 200 * 1024;
+constexpr int kWgMaxBlocks = 512;               // node blocks accumulated by one CTA (see wg_grid)
 
 struct WgShape {
     int mt;          // M tiles handled per CTA (row group of dW = mt * 128 rows)
@@ -245,6 +246,13 @@ int wg_grid(int64_t M, int Nout, int Kin, const WgShape &s, int *n_ranges, int *
     int splits = (int)std::min<int64_t>(std::max<int64_t>(node_blocks, 1), std::max(1, kNumSMs / (*n_ranges * *m_groups)));
     *per_split = (int)((node_blocks + splits - 1) / splits);
     if (*per_split < 1) *per_split = 1;
+    // The tensor core adds into its accumulator with truncation (≈ 2^-26 of the running sum per step, one-sided —
+    // measured in gemm_tc.cu): cap the chain at kWgMaxBlocks node blocks (4 steps each => ≤ 3e-5) and let MORE CTAs than
+    // SMs run in waves; the split partials are then added in fp32 round-to-nearest by the reduce kernel.
+    if (*per_split > kWgMaxBlocks) {                 // whole waves of `splits` CTAs, each at most kWgMaxBlocks long
+        const int64_t waves = (node_blocks + (int64_t)splits * kWgMaxBlocks - 1) / ((int64_t)splits * kWgMaxBlocks);
+        *per_split = (int)((node_blocks + splits * waves - 1) / (splits * waves));
+    }
     splits = (int)std::max<int64_t>(1, (node_blocks + *per_split - 1) / *per_split);
     return splits;
 }
