@@ -248,6 +248,10 @@ int sirgcn_copy_rows(void *dst, int64_t dst_pitch_bytes, const void *src, int64_
  * partials of the splits are summed in split order (bitwise repeatable).  dW / db are fp32.  n_out, k_in, ldy, ldx
  * multiples of 8; workspace: sirgcn_gemm_wgrad_workspace_bytes(m, n_out, k_in) bytes of device scratch. */
 size_t sirgcn_gemm_wgrad_workspace_bytes(int64_t m, int32_t n_out, int32_t k_in);
+/* the launch plan sirgcn_gemm_wgrad would use (host-only, no CUDA call; for tests and sizing): plan[10] =
+ * {node splits, node blocks (64 rows) per split, column ranges, row groups, M tiles per CTA, columns per CTA,
+ *  accumulator columns per M tile, ring stages, TMEM columns, dynamic shared memory bytes} */
+int sirgcn_gemm_wgrad_plan(int64_t m, int32_t n_out, int32_t k_in, int32_t with_bias, int32_t *plan);
 int sirgcn_gemm_wgrad(const void *dy, int64_t ldy, const void *x, int64_t ldx, int64_t m, int32_t n_out, int32_t k_in,
                       int32_t dtype, float *dw, int64_t ld_dw, float *db, void *workspace, size_t workspace_bytes,
                       void *stream);

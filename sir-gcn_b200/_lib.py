@@ -25,7 +25,7 @@ EXPORTS = (
     "sirgcn_edge_subgraph_workspace_bytes", "sirgcn_edge_subgraph",
     "sirgcn_num_tiles", "sirgcn_tiles_build", "sirgcn_rows_build_workspace_bytes", "sirgcn_rows_build",
     "sirgcn_edge_partial_bytes", "sirgcn_edge_fwd", "sirgcn_edge_bwd_q", "sirgcn_edge_bwd_k", "sirgcn_etable_grad",
-    "sirgcn_gemm_tn", "sirgcn_gemm_wgrad_workspace_bytes", "sirgcn_gemm_wgrad", "sirgcn_colsum_workspace_bytes", "sirgcn_colsum", "sirgcn_copy_rows", "sirgcn_mask_scale", "sirgcn_gather_add", "sirgcn_segment_sum", "sirgcn_segment_minmax", "sirgcn_segment_minmax_bwd",
+    "sirgcn_gemm_tn", "sirgcn_gemm_wgrad_workspace_bytes", "sirgcn_gemm_wgrad_plan", "sirgcn_gemm_wgrad", "sirgcn_colsum_workspace_bytes", "sirgcn_colsum", "sirgcn_copy_rows", "sirgcn_mask_scale", "sirgcn_gather_add", "sirgcn_segment_sum", "sirgcn_segment_minmax", "sirgcn_segment_minmax_bwd",
     "sirgcn_peer_alloc", "sirgcn_peer_free", "sirgcn_peer_open", "sirgcn_peer_close", "sirgcn_peer_copy", "sirgcn_peer_push", "sirgcn_peer_push_tma", "sirgcn_peer_barrier",
 )
 

@@ -270,6 +270,19 @@ extern "C" size_t sirgcn_gemm_wgrad_workspace_bytes(int64_t m, int32_t n_out, in
     return (size_t)splits * n_out * ldp * sizeof(float) + 256;
 }
 
+extern "C" int sirgcn_gemm_wgrad_plan(int64_t m, int32_t n_out, int32_t k_in, int32_t with_bias, int32_t *plan) {
+    using namespace sirgcn;
+    SIRGCN_CHECK_ARG(plan && m >= 0 && n_out > 0 && k_in > 0, "bad arguments");
+    const WgShape s = wg_shape(n_out, k_in, with_bias != 0);
+    int nr, mg, per;
+    const int splits = wg_grid(m, n_out, k_in, wg_shape(n_out, k_in, true), &nr, &mg, &per);
+    nr = (k_in + s.nc - 1) / s.nc;
+    const int smem = s.stages * (s.mt * 2 + s.nb) * kWgBox + 2048 + 256 + 1024;
+    const int32_t out[10] = {splits, per, nr, mg, s.mt, s.nc, s.ncp, s.stages, s.tmem_cols, smem};
+    for (int i = 0; i < 10; ++i) plan[i] = out[i];
+    return SIRGCN_OK;
+}
+
 extern "C" int sirgcn_gemm_wgrad(const void *dy, int64_t ldy, const void *x, int64_t ldx, int64_t m, int32_t n_out,
                                  int32_t k_in, int32_t dtype, float *dw, int64_t ld_dw, float *db, void *workspace,
                                  size_t workspace_bytes, void *stream) {

@@ -67,3 +67,28 @@ def test_argument_validation_without_gpu(lib_path):
     assert L.sirgcn_edge_bwd_k(ctypes.byref(a), None) == -1
     with pytest.raises(RuntimeError, match="long_threshold"):
         _lib.check(-1, "sirgcn_edge_bwd_k")
+
+
+def test_wgrad_launch_plan_invariants(lib_path):
+    """sirgcn_gemm_wgrad's host-side plan (no GPU needed): every 64-node block is covered by exactly one split, a CTA
+    never accumulates more than 512 blocks (the tensor core's accumulation truncates: DESIGN §2.4), the accumulators of
+    all M tiles fit the 512 TMEM columns, the ring fits shared memory, and the workspace query matches the plan"""
+    lib = ctypes.CDLL(lib_path)
+    lib.sirgcn_gemm_wgrad_workspace_bytes.restype = ctypes.c_size_t
+    lib.sirgcn_gemm_wgrad_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]
+    plan = (ctypes.c_int32 * 10)()
+    for m in (1, 63, 64, 65, 2944, 100_000, 4_850_000, 6_250_000, 25_000_000, 50_000_000, 2_000_000_000):
+        for n_out, k_in in ((8, 8), (128, 64), (152, 72), (256, 128), (512, 128), (512, 256), (1024, 64), (264, 520)):
+            for bias in (0, 1):
+                assert lib.sirgcn_gemm_wgrad_plan(ctypes.c_int64(m), n_out, k_in, bias, plan) == 0
+                splits, per, n_ranges, m_groups, mt, nc, ncp, stages, tmem, smem = list(plan)
+                blocks = (m + 63) // 64
+                assert splits >= 1 and 1 <= per <= 512, (m, n_out, k_in, per)
+                assert (splits - 1) * per < blocks <= splits * per, (m, blocks, splits, per)     # no empty split
+                assert 1 <= mt <= 4 and m_groups * mt * 128 >= n_out and n_ranges * nc >= k_in
+                assert nc % 16 == 0 and 16 <= nc <= 256 and ncp == nc + 16 * bias
+                assert mt * ncp + 16 <= tmem <= 512 and tmem & (tmem - 1) == 0
+                assert 2 <= stages <= 8 and smem <= 227 * 1024
+                need = lib.sirgcn_gemm_wgrad_workspace_bytes(ctypes.c_int64(m), n_out, k_in)
+                ldp = (k_in + 3) // 4 * 4 + 4
+                assert need >= splits * n_out * ldp * 4
