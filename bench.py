@@ -298,6 +298,18 @@ def scaled_shape(args, w):
 # ------------------------------------------------------------------------------------------------
 # parity gate of the partitioned path (N > 1), run before anything is timed
 # ------------------------------------------------------------------------------------------------
+def parity_verdict(gated, loose, tol, tol_loose, device):
+    """(worst gated error over ALL ranks, passed): every rank contributes what it measured — rank 0 alone holds the
+    oracle leg — and every rank gets the SAME answer, so that all of them take the same branch afterwards (a rank that
+    exits alone leaves the others hanging in the next collective: round 2 lost its 8-GPU budget to exactly that)."""
+    import torch.distributed as dist
+    ratio = max([v / tol for v in gated.values()] + [v / tol_loose for v in loose.values()])
+    t = torch.tensor([max(gated.values()), ratio], device=device, dtype=torch.float64)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0]), bool(float(t[1]) <= 1.0)
+
+
 def partition_parity_check(args, w, layers, dev, rank, world):
     """The L-layer stack on a ~1 M-edge hashed power-law graph through THE transport and schedule that will be timed,
     against (a) the single-rank kernels on the whole graph (every rank) and (b) the fp64 CPU oracle (rank 0): output
@@ -385,14 +397,10 @@ def partition_parity_check(args, w, layers, dev, rank, world):
     # ONE verdict for all ranks (every rank must take the same branch afterwards): the worst error / tolerance ratio
     tol = 2e-2 if dtype != torch.float32 else 1e-5
     tol_loose = 5e-2        # 16-bit gradients against fp64 in the Frobenius norm: catches a wrong result, not rounding
-    ratio = max([v / tol for v in gated.values()] + [v / tol_loose for v in loose.values()])
-    t = torch.tensor([max(gated.values()), ratio], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    res["max_rel_err"] = float(t[0])
+    res["max_rel_err"], res["passed"] = parity_verdict(gated, loose, tol, tol_loose, dev)
     res["gated"] = sorted(gated)
     res["tolerance"] = tol
     res["gated_frobenius"], res["tolerance_frobenius"] = sorted(loose), tol_loose
-    res["passed"] = bool(float(t[1]) <= 1.0)
     for p in params:
         p.grad = None
     del whole, part, x, gout, out1, dx1, dw1, outp, dxp, dwp

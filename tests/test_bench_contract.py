@@ -38,3 +38,42 @@ def test_algorithmic_bytes_match_the_survey():
     E, N, r = 6_400, 2_944, 64 * 4
     tot = sum(bench.edge_bytes(k, E, N, r, eps=r) for k in ("sirgcn_edge_fwd", "sirgcn_edge_bwd_q", "sirgcn_edge_bwd_k"))
     assert round(tot / E) == 2634
+
+
+def _verdict_worker(rank, world, port, ret):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bench
+        ok = {"out": 0.0, "dX": 4.5e-3, "dW": 5.3e-3}
+        # only rank 0 holds the oracle leg; in case 2 it alone sees a failing number
+        c1 = bench.parity_verdict(dict(ok, **({"oracle_out": 3.9e-3} if rank == 0 else {})),
+                                  {"oracle_dX_frobenius": 8e-3} if rank == 0 else {}, 2e-2, 5e-2, "cpu")
+        c2 = bench.parity_verdict(dict(ok, **({"oracle_out": 6e-2} if rank == 0 else {})), {}, 2e-2, 5e-2, "cpu")
+        c3 = bench.parity_verdict(dict(ok, dX=(3e-2 if rank == world - 1 else 1e-3)), {}, 2e-2, 5e-2, "cpu")
+        c4 = bench.parity_verdict(ok, {"oracle_dX_frobenius": 0.2} if rank == 0 else {}, 2e-2, 5e-2, "cpu")
+        ret[rank] = (c1, c2, c3, c4)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_parity_gate_verdict_is_the_same_on_every_rank():
+    """the N>1 parity gate of bench.py: whatever a single rank measured, ALL ranks get the same verdict"""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    world = 3
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_verdict_worker, args=(world, port, ret), nprocs=world, join=True)
+        got = dict(ret)
+    assert len(got) == world and all(got[r] == got[0] for r in got)
+    c1, c2, c3, c4 = got[0]
+    assert c1 == (5.3e-3, True)
+    assert c2[1] is False and abs(c2[0] - 6e-2) < 1e-12
+    assert c3[1] is False and abs(c3[0] - 3e-2) < 1e-12
+    assert c4[1] is False and abs(c4[0] - 5.3e-3) < 1e-12          # failed on the Frobenius leg alone
