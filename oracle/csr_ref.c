@@ -7,9 +7,9 @@
  * source-major ordering used by the backward scatter (index_add_ over src,
  * SURVEY.md K11), and the clamp(min=1)^-1/2 norms of conv.py:51-57.
  *
- * PARITY UNPINNED against DGL (DGL 2.1.0, requirements.txt:1, is not installed and
- * the reference has no fixtures); pinned against torch.sort(stable=True) in
- * tests/test_oracle_pins.py.
+ * PARITY UNPINNED against DGL for this file (DGL 2.1.0, requirements.txt:1, is not installed and
+ * the reference has no fixtures: the stable tie order is DGL's documented behaviour, not a value the
+ * reference's own code produces); pinned against torch.sort(stable=True) in tests/test_oracle_pins.py.
  *
  * Plain C, single thread, O(N+E) counting sort.  Built by oracle/Makefile into
  * oracle/_build/libcsr_ref.so.

@@ -4,7 +4,9 @@
  * (message_func :43-47 / :109-113 and update_all with fn.sum / fn.mean :63 / :130), written as explicit loops over
  * the COO edge list in double precision, with the derivative written out by hand instead of obtained from autograd.
  * tests/test_oracle_pins.py checks it against oracle/sirconv_ref.py (torch ops + autograd): two restatements that
- * share no code must agree to 1e-12.  PARITY UNPINNED against DGL itself (DGL is not installable here).
+ * share no code must agree to 1e-12 (1e-6 for 'sym': torch.pow(x,-0.5) vs IEEE 1/sqrt(x) in fp32).  The torch restatement
+ * is itself pinned on the reference's own code executed through tests/fake_dgl (see its header); DGL's own arithmetic
+ * stays unpinned (DGL is not installable here).
  *
  *   z_e  = q[dst_e] + k[src_e] (+ e_e)                                   conv.py:45 / :111
  *   m_e  = c_e * act(z_e),  c_e = out_norm[src_e] * in_norm[dst_e]       conv.py:45-46, :51-57 ('sym'; 1 otherwise)
